@@ -1,0 +1,144 @@
+/*
+ * naf_b200 -- C ABI of the B200-native cross-scale neighbourhood-attention forward.
+ *
+ * This is the drop-in boundary for the hot path of valeoai/NAF.  The reference binds this path
+ * through Python (PyTorch + the third-party NATTEN extension); every entry point below names the
+ * reference interface it replaces.  All pointers are DEVICE pointers unless stated otherwise,
+ * all tensors are fp32, all strides are in ELEMENTS.  No entry point allocates, frees or
+ * synchronises; work is enqueued on `stream` (a cudaStream_t passed as void*).  Every function
+ * returns a naf_status; a human-readable message for the last failure on the calling thread is
+ * available from naf_last_error().
+ *
+ * Canonical device layouts ("pixel-major", channels innermost):
+ *   guidance  x / q : (B, Ho, Wo, D)   channel stride 1, pixel strides free (>= D, 16 B aligned)
+ *   keys      k     : (B, h,  w,  D)   contiguous
+ *   values    v     : (B, h,  w,  C)   contiguous
+ *   output    out   : (B, Ho, Wo, C)   contiguous  (the reference also returns pixel-major
+ *                                       storage: src/layers/attentions.py:75 is a permuted view)
+ *   scores          : (B, n, Ho, Wo, K*K) contiguous, tap order t_h*K + t_w
+ */
+#ifndef NAF_B200_H_
+#define NAF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NAF_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NAF_API __attribute__((visibility("default")))
+#else
+#define NAF_API
+#endif
+
+typedef enum naf_status {
+  NAF_OK = 0,
+  NAF_ERR_BAD_SHAPE = 1,      /* non-positive size, C or D not divisible by heads, ...          */
+  NAF_ERR_UNSUPPORTED = 2,    /* valid request this build has no kernel for                      */
+  NAF_ERR_WINDOW = 3,         /* kernel_size even / < 1, or kernel_size*dilation > target axis  */
+  NAF_ERR_ALIGNMENT = 4,      /* pointer or stride not aligned as the layout above requires     */
+  NAF_ERR_NULL = 5,           /* required pointer is NULL                                        */
+  NAF_ERR_CUDA = 6            /* CUDA runtime error at launch (message in naf_last_error)       */
+} naf_status;
+
+/* ABI version of the loaded library (== NAF_ABI_VERSION of the header it was built from). */
+NAF_API int naf_abi_version(void);
+
+/* Message for the last non-OK status returned on this host thread ("" if none). */
+NAF_API const char* naf_last_error(void);
+
+/* 1 if the library was compiled with the tcgen05/TMEM tensor-core path, 0 if SIMT only. */
+NAF_API int naf_has_tensor_path(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout packing: (B, C, H, W) with arbitrary element strides -> (B, H, W, C) contiguous.
+ * Replaces the `rearrange(x, "b (n d) h w -> b h w n d")` / `.to(dtype)` layout steps of
+ * reference src/layers/attentions.py:49-51,59 (without the nearest-exact replication: K and V
+ * stay at low resolution).
+ * ---------------------------------------------------------------------------------------- */
+NAF_API int naf_pack_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W,
+                      int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * RoPE + key pooling pre-pass.
+ *   q      = RoPE(x)                      reference src/layers/rope.py:155-174 (eval branch)
+ *   k_out  = adaptive_avg_pool2d(q,(h,w)) reference src/model/naf.py:63-69,108
+ * x is pixel-major with channel stride 1.  The four tables are what RoPE.rotate builds
+ * (src/layers/rope.py:139-146), factored per axis: cos/sin of 2*pi*coord/period for the rows
+ * (`*_y`, shape (Ho, P)) and the columns (`*_x`, shape (Wo, P)), P = (D/rope_heads)/4.
+ * q_out may be NULL (keys only); when given it receives the rotated map, contiguous
+ * (B,Ho,Wo,D).  If all four tables are NULL, x is taken as already rotated.
+ * Pooling bins follow ATen: rows [floor(i*Ho/h), ceil((i+1)*Ho/h)).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct naf_kpool_params {
+  const float* x;        /* (B,Ho,Wo,D) */
+  float* k_out;          /* (B,h,w,D) contiguous */
+  float* q_out;          /* NULL or (B,Ho,Wo,D) contiguous */
+  const float* cos_y;    /* (Ho,P) */
+  const float* sin_y;
+  const float* cos_x;    /* (Wo,P) */
+  const float* sin_x;
+  int32_t B, D, Ho, Wo, h, w;
+  int32_t rope_heads;    /* D % (4*rope_heads) == 0 */
+  int64_t x_stride_b, x_stride_y, x_stride_x; /* elements */
+} naf_kpool_params;
+
+NAF_API int naf_rope_kpool_f32(const naf_kpool_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Cross-scale neighbourhood attention forward.
+ * Replaces reference CrossAttention.forward (src/layers/attentions.py:53-75) together with
+ * legacy_attention (:16-29) and the NATTEN functionals it calls (na2d_qk :20, na2d_av :24, or
+ * fused na2d :72):
+ *   s[t,u] = scale * <q[b,y,x,head], k[b,row_tap[y][t],col_tap[x][u],head]>
+ *   p      = softmax_{t,u}(s)
+ *   out[b,y,x,head] = sum_{t,u} p[t,u] * v[b,row_tap[y][t],col_tap[x][u],head]
+ * row_tap (Ho,K) / col_tap (Wo,K) are int32 DEVICE tables holding the composition of NATTEN's
+ * shifted dilated window with F.interpolate(mode="nearest-exact").  They may
+ * both be NULL iff Ho % h == 0 and Wo % w == 0: then the window of a pixel is the clamped
+ * low-resolution window  clamp(y/(Ho/h) - K/2, 0, h-K) + t  shared by its whole cell.
+ * If the rope tables are non-NULL, `q` holds the UN-rotated map and RoPE is applied on the fly
+ * (requires rope head dim == D/heads); otherwise q is used as is.
+ * `scores` (optional) receives the scaled pre-softmax logits (reference return_weights=True,
+ * src/layers/attentions.py:27-28).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct naf_xattn_params {
+  const float* q;        /* (B,Ho,Wo,D) channel stride 1 */
+  const float* k;        /* (B,h,w,D) contiguous */
+  const float* v;        /* (B,h,w,C) contiguous */
+  float* out;            /* (B,Ho,Wo,C) contiguous */
+  float* scores;         /* NULL or (B,heads,Ho,Wo,K*K) */
+  const int32_t* row_tap;/* NULL or (Ho,K) */
+  const int32_t* col_tap;/* NULL or (Wo,K) */
+  const float* cos_y;    /* NULL or (Ho, D/heads/4) */
+  const float* sin_y;
+  const float* cos_x;    /* NULL or (Wo, D/heads/4) */
+  const float* sin_x;
+  int32_t B, D, C, heads, Ho, Wo, h, w, K;
+  float scale;           /* (D/heads)^-0.5 in the reference (src/layers/attentions.py:46) */
+  int64_t q_stride_b, q_stride_y, q_stride_x; /* elements */
+  int32_t algo;          /* NAF_ALGO_* ; AUTO picks the fastest kernel that supports the request */
+} naf_xattn_params;
+
+enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2, NAF_ALGO_CELL_TC = 3 };
+
+NAF_API int naf_xattn_fwd_f32(const naf_xattn_params* p, void* stream);
+
+/* Which NAF_ALGO_* would AUTO select for these parameters (no launch).  Negative = -naf_status. */
+NAF_API int naf_xattn_select_algo(const naf_xattn_params* p);
+
+/* Test hook for the "bit-exact neighbourhood index" requirement: writes, for every target pixel,
+ * the K*K linear low-res cell indices (row*w + col) the attention kernels gather from, using the
+ * SAME device index code as the kernels.  idx_out: (Ho, Wo, K*K) int32.  Tables as above. */
+NAF_API int naf_xattn_dump_taps_i32(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap,
+                            int Ho, int Wo, int h, int w, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAF_B200_H_ */

@@ -1,0 +1,67 @@
+"""Build libnaf_b200.so in-tree with nvcc for sm_100a (no torch headers, pure C ABI).
+
+    python -m naf_b200.csrc.build [--force] [--verbose]
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+LIB = os.path.join(HERE, "libnaf_b200.so")
+STAMP = os.path.join(HERE, ".build_stamp")
+SOURCES = ["naf_abi.cu", "naf_pack.cu", "naf_kpool.cu", "naf_xattn_generic.cu", "naf_xattn_simt.cu",
+           "naf_xattn_tc.cu"]
+HEADERS = ["naf_common.cuh", os.path.join(ROOT, "include", "naf_b200.h")]
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for f in SOURCES + HEADERS + [os.path.abspath(__file__)]:
+        path = f if os.path.isabs(f) else os.path.join(HERE, f)
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def command(verbose: bool = False) -> list[str]:
+    cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
+           "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "-shared",
+           "-I", os.path.join(ROOT, "include"), "-I", HERE, "-DNAF_BUILDING_LIB",
+           "-o", LIB]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(HERE, s) for s in SOURCES]
+    return cmd
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    dig = _digest()
+    if not force and os.path.isfile(LIB) and os.path.isfile(STAMP):
+        with open(STAMP) as fh:
+            if fh.read().strip() == dig:
+                return LIB
+    res = subprocess.run(command(verbose), capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libnaf_b200.so")
+    with open(STAMP, "w") as fh:
+        fh.write(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

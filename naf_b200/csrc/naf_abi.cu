@@ -1,0 +1,164 @@
+// extern "C" entry points of libnaf_b200.so: argument validation, algorithm selection, error
+// reporting.  See include/naf_b200.h for the contract of every function.
+#include <cstring>
+
+#include "naf_common.cuh"
+
+namespace naf {
+
+char* last_error_buffer() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+int fail(naf_status code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(last_error_buffer(), 512, fmt, ap);
+  va_end(ap);
+  return static_cast<int>(code);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess)
+    return fail(NAF_ERR_CUDA, "%s: CUDA error %d (%s)", what, int(e), cudaGetErrorString(e));
+  return NAF_OK;
+}
+
+static int validate_xattn(const naf_xattn_params& p) {
+  NAF_REQUIRE(p.q && p.k && p.v && p.out, NAF_ERR_NULL, "xattn: q, k, v and out must be non-NULL");
+  NAF_REQUIRE(p.B > 0 && p.D > 0 && p.C > 0 && p.heads > 0 && p.Ho > 0 && p.Wo > 0 && p.h > 0 &&
+                  p.w > 0,
+              NAF_ERR_BAD_SHAPE, "xattn: sizes must be positive");
+  NAF_REQUIRE(p.D % p.heads == 0, NAF_ERR_BAD_SHAPE, "dim must be divisible by num_heads");
+  NAF_REQUIRE(p.C % p.heads == 0, NAF_ERR_BAD_SHAPE,
+              "value channels (%d) must be divisible by num_heads (%d)", p.C, p.heads);
+  NAF_REQUIRE(p.K >= 1 && (p.K & 1), NAF_ERR_WINDOW, "kernel_size must be odd and >= 1, got %d",
+              p.K);
+  const bool have_tables = p.row_tap && p.col_tap;
+  NAF_REQUIRE(have_tables || (!p.row_tap && !p.col_tap), NAF_ERR_NULL,
+              "xattn: row_tap and col_tap must both be given or both be NULL");
+  if (!have_tables) {
+    NAF_REQUIRE(p.Ho % p.h == 0 && p.Wo % p.w == 0, NAF_ERR_BAD_SHAPE,
+                "xattn: tap tables are required when the target size is not a multiple of the "
+                "feature size");
+  }
+  // NATTEN's constraint kernel_size * dilation <= axis length (dilation = Ho // h)
+  NAF_REQUIRE(p.Ho / p.h >= 1 && p.Wo / p.w >= 1 && int64_t(p.K) * (p.Ho / p.h) <= p.Ho &&
+                  int64_t(p.K) * (p.Wo / p.w) <= p.Wo,
+              NAF_ERR_WINDOW,
+              "kernel_size*dilation exceeds the target size (K=%d, target %dx%d, features %dx%d)",
+              p.K, p.Ho, p.Wo, p.h, p.w);
+  const int nrope = (p.cos_y != nullptr) + (p.sin_y != nullptr) + (p.cos_x != nullptr) +
+                    (p.sin_x != nullptr);
+  NAF_REQUIRE(nrope == 0 || nrope == 4, NAF_ERR_NULL,
+              "xattn: rope tables must be all given or all NULL");
+  if (nrope == 4)
+    NAF_REQUIRE((p.D / p.heads) % 4 == 0, NAF_ERR_BAD_SHAPE,
+                "xattn: on-the-fly RoPE needs head dim %% 4 == 0");
+  NAF_REQUIRE(p.q_stride_x >= p.D && p.q_stride_y >= 0 && p.q_stride_b >= 0, NAF_ERR_BAD_SHAPE,
+              "xattn: bad q strides");
+  return NAF_OK;
+}
+
+static int select_algo(const naf_xattn_params& p, bool explain) {
+  const char* why = "";
+  if (p.algo == NAF_ALGO_GENERIC) return NAF_ALGO_GENERIC;
+  if (p.algo == NAF_ALGO_CELL_TC) {
+    if (xattn_cell_tc_supported(p, &why)) return NAF_ALGO_CELL_TC;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: tensor-core cell kernel unsupported: %s", why);
+  }
+  if (p.algo == NAF_ALGO_CELL_SIMT) {
+    if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: SIMT cell kernel unsupported: %s", why);
+  }
+  if (p.algo != NAF_ALGO_AUTO) return -fail(NAF_ERR_UNSUPPORTED, "xattn: unknown algo %d", p.algo);
+  (void)explain;
+  if (xattn_cell_tc_supported(p, &why)) return NAF_ALGO_CELL_TC;
+  if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
+  return NAF_ALGO_GENERIC;
+}
+
+}  // namespace naf
+
+using namespace naf;
+
+extern "C" {
+
+int naf_abi_version(void) { return NAF_ABI_VERSION; }
+
+const char* naf_last_error(void) { return last_error_buffer(); }
+
+int naf_has_tensor_path(void) {
+#ifdef NAF_WITH_TC
+  return 1;
+#else
+  return 0;
+#endif
+}
+
+int naf_pack_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, int64_t stride_b,
+                      int64_t stride_c, int64_t stride_h, int64_t stride_w, void* stream) {
+  NAF_REQUIRE(src && dst, NAF_ERR_NULL, "pack_nhwc: NULL pointer");
+  NAF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "pack_nhwc: sizes must be positive");
+  return launch_pack_nhwc(src, dst, B, C, H, W, stride_b, stride_c, stride_h, stride_w,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int naf_rope_kpool_f32(const naf_kpool_params* pp, void* stream) {
+  NAF_REQUIRE(pp, NAF_ERR_NULL, "rope_kpool: NULL params");
+  const naf_kpool_params& p = *pp;
+  NAF_REQUIRE(p.x && (p.k_out || p.q_out), NAF_ERR_NULL, "rope_kpool: x and one output required");
+  NAF_REQUIRE(p.B > 0 && p.D > 0 && p.Ho > 0 && p.Wo > 0, NAF_ERR_BAD_SHAPE,
+              "rope_kpool: sizes must be positive");
+  NAF_REQUIRE(!p.k_out || (p.h > 0 && p.w > 0), NAF_ERR_BAD_SHAPE, "rope_kpool: bad pooled size");
+  const int nrope = (p.cos_y != nullptr) + (p.sin_y != nullptr) + (p.cos_x != nullptr) +
+                    (p.sin_x != nullptr);
+  NAF_REQUIRE(nrope == 0 || nrope == 4, NAF_ERR_NULL,
+              "rope_kpool: rope tables must be all given or all NULL");
+  if (nrope == 4)
+    NAF_REQUIRE(p.rope_heads > 0 && p.D % (4 * p.rope_heads) == 0, NAF_ERR_BAD_SHAPE,
+                "rope_kpool: embed_dim %% (4*num_heads) must be 0");
+  NAF_REQUIRE(p.x_stride_x >= p.D, NAF_ERR_BAD_SHAPE, "rope_kpool: bad x strides");
+  return launch_rope_kpool(p, static_cast<cudaStream_t>(stream));
+}
+
+int naf_xattn_select_algo(const naf_xattn_params* pp) {
+  if (!pp) return -fail(NAF_ERR_NULL, "xattn: NULL params");
+  int rc = validate_xattn(*pp);
+  if (rc != NAF_OK) return -rc;
+  return select_algo(*pp, true);
+}
+
+int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
+  NAF_REQUIRE(pp, NAF_ERR_NULL, "xattn: NULL params");
+  const naf_xattn_params& p = *pp;
+  int rc = validate_xattn(p);
+  if (rc != NAF_OK) return rc;
+  const int algo = select_algo(p, false);
+  if (algo < 0) return -algo;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (algo) {
+    case NAF_ALGO_CELL_TC:
+      return launch_xattn_cell_tc(p, st);
+    case NAF_ALGO_CELL_SIMT:
+      return launch_xattn_cell_simt(p, st);
+    default:
+      return launch_xattn_generic(p, st);
+  }
+}
+
+int naf_xattn_dump_taps_i32(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap,
+                            int Ho, int Wo, int h, int w, int K, void* stream) {
+  NAF_REQUIRE(idx_out, NAF_ERR_NULL, "dump_taps: NULL output");
+  NAF_REQUIRE(Ho > 0 && Wo > 0 && h > 0 && w > 0 && K >= 1 && (K & 1), NAF_ERR_BAD_SHAPE,
+              "dump_taps: bad sizes");
+  const bool have = row_tap && col_tap;
+  NAF_REQUIRE(have || (Ho % h == 0 && Wo % w == 0 && !row_tap && !col_tap), NAF_ERR_BAD_SHAPE,
+              "dump_taps: tables required for non-integer ratios");
+  return launch_dump_taps(idx_out, row_tap, col_tap, Ho, Wo, h, w, K,
+                          static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,41 @@
+"""Cross-scale neighbourhood attention operator, CUDA-backed.
+
+Drop-in for the reference `CrossAttention` (src/layers/attentions.py:32-75): same constructor,
+same `forward(q, k, v, image=None, return_weights=False)`, same side effect (`self.dilation`),
+same output -- a (B, C, Ho, Wo) permuted view over pixel-major storage.  Where the reference
+replicates K and V to the target resolution (`_resize`, :48-51) and calls NATTEN on the dilated
+high-resolution grid (:20,24,72), this operator hands the low-resolution K and V straight to
+`naf_xattn_fwd_f32`, which evaluates the identical neighbourhoods through integer tap tables
+(`naf_b200/taps.py`).
+"""
+from __future__ import annotations
+
+from torch import nn
+
+from .. import _lib, ops
+
+
+class CrossAttention(nn.Module):
+    def __init__(self, dim, num_heads, kernel_size=(9, 9), **kwargs):
+        super().__init__()
+        assert dim % num_heads == 0, "dim must be divisible by num_heads"
+        self.num_heads = num_heads
+        self.kernel_size = kernel_size
+        self.scale = (dim // num_heads) ** -0.5
+        self.algo = _lib.ALGO_AUTO
+
+    def _square_kernel(self) -> int:
+        ks = self.kernel_size
+        if isinstance(ks, (tuple, list)):
+            if len(ks) != 2 or int(ks[0]) != int(ks[1]):
+                raise NotImplementedError(f"naf_b200 supports square windows only, got {ks}")
+            return int(ks[0])
+        return int(ks)
+
+    def forward(self, q, k, v, image=None, return_weights=False, rope_tables=None, **kwargs):
+        hq, wq = q.shape[-2:]
+        hk, wk = k.shape[-2:]
+        self.dilation = (hq // hk, wq // wk)
+        res = ops.xattn(q, k, v, self.num_heads, self._square_kernel(), scale=self.scale,
+                        rope_tables=rope_tables, return_scores=return_weights, algo=self.algo)
+        return res

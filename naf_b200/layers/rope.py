@@ -1,0 +1,98 @@
+"""Axial 2-D rotary position embedding (DINOv3 style), CUDA-backed.
+
+Mirrors the reference operator `RoPE` (src/layers/rope.py:39-174): same constructor keywords, the
+same persistent `periods` buffer (so `state_dict` keys match), the same `forward(x, layout)`.
+The rotation itself runs in `naf_rope_kpool_f32`; inside `NAF.forward` it is fused further (the
+attention kernel rotates q on the fly and the key pre-pass rotates while it pools), so this
+module's `forward` is only used when somebody calls RoPE on its own.
+
+Inference scope: the train-time coordinate augmentations (`shift_coords`, `jitter_coords`,
+`rescale_coords`; src/layers/rope.py:108-124) are accepted and stored but calling the module in
+training mode with any of them set raises -- the forward-only tier does not implement them.
+"""
+from __future__ import annotations
+
+import math
+from typing import Literal, Optional
+
+import torch
+from torch import Tensor, nn
+
+from .. import ops
+
+
+class RoPE(nn.Module):
+    def __init__(
+        self,
+        embed_dim: int,
+        *,
+        num_heads: int,
+        base: Optional[float] = 100.0,
+        min_period: Optional[float] = None,
+        max_period: Optional[float] = None,
+        normalize_coords: Literal["min", "max", "separate"] = "separate",
+        shift_coords: Optional[float] = None,
+        jitter_coords: Optional[float] = None,
+        rescale_coords: Optional[float] = None,
+        dtype: Optional[torch.dtype] = None,
+        device: Optional[torch.device] = None,
+    ):
+        super().__init__()
+        assert embed_dim % (4 * num_heads) == 0
+        has_range = min_period is not None and max_period is not None
+        if (base is None) == (not has_range):
+            raise ValueError("Either `base` or `min_period`+`max_period` must be provided.")
+        self.num_heads = num_heads
+        self.base = base
+        self.min_period = min_period
+        self.max_period = max_period
+        self.D_head = embed_dim // num_heads
+        self.normalize_coords = normalize_coords
+        self.shift_coords = shift_coords
+        self.jitter_coords = jitter_coords
+        self.rescale_coords = rescale_coords
+        self.dtype = dtype
+        self.register_buffer("periods", torch.empty(self.D_head // 4, device=device, dtype=dtype),
+                             persistent=True)
+        self._init_weights()
+        self._table_key = None
+        self._tables = None
+
+    def _init_weights(self) -> None:
+        n = self.D_head // 4
+        dev = self.periods.device
+        if self.base is not None:
+            exponent = 2 * torch.arange(n, device=dev, dtype=self.dtype) / (self.D_head // 2)
+            periods = self.base ** exponent
+        else:
+            periods = torch.logspace(math.log10(self.min_period), math.log10(self.max_period), steps=n)
+        self.periods.data = periods
+
+    # -- tables -----------------------------------------------------------------------------
+    def axis_tables(self, H: int, W: int):
+        """(cos_y, sin_y, cos_x, sin_x) for an (H, W) map, cached per shape/device."""
+        if self.normalize_coords != "separate":
+            if self.normalize_coords in ("min", "max"):
+                raise NotImplementedError(
+                    "naf_b200 RoPE implements normalize_coords='separate' (the only mode NAF uses)")
+            raise ValueError(f"Unknown normalize_coords: {self.normalize_coords}")
+        if self.training and any(v is not None for v in (self.shift_coords, self.jitter_coords, self.rescale_coords)):
+            raise NotImplementedError(
+                "naf_b200 is forward/inference only: RoPE coordinate augmentation is a training "
+                "feature; call .eval() first")
+        key = (H, W, self.periods.device, self.periods.data_ptr(), self.periods._version)
+        if key != self._table_key:
+            self._tables = ops.rope_axis_tables(H, W, self.periods.to(torch.float32))
+            self._table_key = key
+        return self._tables
+
+    def forward(self, x: Tensor, layout: str = "spatial") -> Tensor:
+        B, D, H, W = x.shape
+        if D != self.D_head * self.num_heads:
+            raise ValueError(f"expected {self.D_head * self.num_heads} channels, got {D}")
+        _, q = ops.rope_kpool(x, self.axis_tables(H, W), self.num_heads, pooled_hw=None, want_q=True)
+        if layout == "spatial":
+            return q
+        if layout == "flatten":
+            return q.permute(0, 2, 3, 1).reshape(B, H, W, self.num_heads, self.D_head)
+        return q.permute(0, 2, 3, 1).reshape(B, H * W, self.num_heads, self.D_head).permute(0, 2, 1, 3)

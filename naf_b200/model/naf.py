@@ -1,0 +1,114 @@
+"""NAF upsampler: forward of the reference `src/model/naf.py` rebuilt around the B200 kernels.
+
+Module tree, constructor keywords and `state_dict` keys are those of the reference (`NAF`,
+`ImageEncoder`, `QueryEncoder`, `KeyEncoder`; src/model/naf.py:11-116) so released checkpoints
+load with `strict=True`.  The data flow differs:
+
+    reference                                          here
+    ---------                                          ----
+    conv encoder -> adaptive pool            (ATen)    same library ops, channels_last storage
+    RoPE: ~12 elementwise passes over Q      (ATen)    folded into the two kernels below
+    K = adaptive_avg_pool2d(RoPE(x))         (ATen)    naf_rope_kpool_f32   (reads x once)
+    nearest-exact K,V to target res + NATTEN           naf_xattn_fwd_f32    (reads x once, rotates
+      QK / softmax / AV on the dilated grid                                  on the fly, low-res K,V
+                                                                             windows in smem)
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .. import ops
+from ..layers import CrossAttention, RoPE, encoder
+
+
+class ImageEncoder(nn.Module):
+    def __init__(self, in_channels=3, out_channels=256, heads_rope=1, use_encoder=True,
+                 rope_base=None, rope_rescale=None, img_layers=2):
+        super().__init__()
+        self.use_encoder = use_encoder
+        self.out_channels = out_channels
+        half = out_channels // 2
+        self.encoder = encoder(in_channels, half, kernel_size=1, ks_res=1, num_layers=img_layers)
+        self.sem_encoder = encoder(in_channels, half, kernel_size=3, ks_res=3, num_layers=img_layers)
+        self.rope = RoPE(embed_dim=out_channels, num_heads=heads_rope, base=rope_base,
+                         rescale_coords=rope_rescale)
+
+    @staticmethod
+    def encoder_resolution(in_hw, out_hw):
+        """Resolution the conv stack runs at: the guidance image is capped at 4x the target
+        (src/model/naf.py:39-48, including its mixed H/W `min`)."""
+        (Hi, Wi), (Ho, Wo) = in_hw, out_hw
+        if Hi > 4 * Ho or Wi > 4 * Wo:
+            return min(Hi, 4 * Ho, 4 * Wo), min(Wi, 4 * Wo, 4 * Ho)
+        return Hi, Wi
+
+    def forward_encoder(self, x, output_size):
+        if x.is_cuda:
+            x = x.contiguous(memory_format=torch.channels_last)
+        if self.use_encoder:
+            x = torch.cat([self.encoder(x), self.sem_encoder(x)], dim=1)
+        if tuple(x.shape[-2:]) != tuple(int(s) for s in output_size):
+            x = F.adaptive_avg_pool2d(x, output_size=output_size)  # identity when sizes match
+        return x
+
+    def guidance(self, image, output_size):
+        """Pooled, UN-rotated guidance map (B, D, Ho, Wo)."""
+        Ho, Wo = int(output_size[0]), int(output_size[1])
+        size = self.encoder_resolution(image.shape[-2:], (Ho, Wo))
+        if size != tuple(image.shape[-2:]):
+            image = F.interpolate(image, size=size, mode="bilinear", align_corners=False)
+        return self.forward_encoder(image, (Ho, Wo))
+
+    def forward(self, x, output_size):
+        return self.rope(self.guidance(x, output_size))
+
+
+class QueryEncoder(nn.Module):
+    def forward(self, x):
+        return x
+
+
+class KeyEncoder(nn.Module):
+    """K = block mean of the rotated guidance map at the feature resolution."""
+
+    def forward(self, x, features):
+        k, _ = ops.rope_kpool(x, None, 1, pooled_hw=features.shape[-2:], want_q=False)
+        return k
+
+
+class NAF(nn.Module):
+    def __init__(self, dim=256, heads_attn=4, heads_rope=4, kernel_size=9, use_encoder=True,
+                 rope_base=100.0, rope_rescale=2.0, img_layers=2, **kwargs):
+        super().__init__()
+        self.image_encoder = ImageEncoder(in_channels=3, out_channels=dim, heads_rope=heads_rope,
+                                          use_encoder=use_encoder, rope_base=rope_base,
+                                          img_layers=img_layers, rope_rescale=rope_rescale)
+        self.query_encoder = QueryEncoder()
+        self.key_encoder = KeyEncoder()
+        self.upsampler = CrossAttention(dim=dim, num_heads=heads_attn,
+                                        kernel_size=(kernel_size, kernel_size))
+
+    def upsample_from_guidance(self, x, features, return_weights=False):
+        """The hot path proper: pooled un-rotated guidance x (B,D,Ho,Wo) + features (B,C,h,w)
+        -> (B,C,Ho,Wo).  Two kernel launches (+ one tiny packing launch for V)."""
+        rope = self.image_encoder.rope
+        Ho, Wo = x.shape[-2:]
+        tables = rope.axis_tables(Ho, Wo)
+        D = x.shape[1]
+        fused = rope.D_head == D // self.upsampler.num_heads
+        k, q = ops.rope_kpool(x, tables, rope.num_heads, pooled_hw=features.shape[-2:],
+                              want_q=not fused)
+        if fused:
+            return self.upsampler(x, k, features, return_weights=return_weights, rope_tables=tables)
+        return self.upsampler(q, k, features, return_weights=return_weights)
+
+    def forward(self, image, features, output_size, return_weights=False, *args, **kwargs):
+        if torch.is_grad_enabled() and (features.requires_grad or image.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            if torch.is_grad_enabled() and self.training:
+                raise RuntimeError("naf_b200.NAF is forward-only: use torch.no_grad() and .eval()")
+        with torch.no_grad():
+            x = self.image_encoder.guidance(image, output_size)
+            return self.upsample_from_guidance(x, features, return_weights=return_weights)

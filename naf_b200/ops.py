@@ -1,0 +1,251 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, kernels from
+libnaf_b200.so in between.  PyTorch is used for device memory, streams and (tiny) table maths
+only -- every pass over the big tensors is one of our CUDA kernels.
+
+Layout convention: public tensors are NCHW-*shaped* like the reference's; internally everything
+is "pixel-major" (channels innermost).  A channels_last NCHW tensor already IS pixel-major, so
+`as_pixel_major` is free for it; anything else goes through the packing kernel once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib, taps
+
+
+# ------------------------------------------------------------------------------------ helpers
+def _require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "naf_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback "
+                f"(got a tensor on {t.device})")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {dev} vs {t.device}")
+    return dev
+
+
+def _no_grad_guard(*tensors: torch.Tensor) -> None:
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            "naf_b200 implements the forward pass only: call it under torch.no_grad() / "
+            "torch.inference_mode(), or detach the inputs")
+
+
+def _stream(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def is_pixel_major(t: torch.Tensor) -> bool:
+    """NCHW-shaped tensor whose channel stride is 1 and whose pixel strides are 16 B friendly."""
+    if t.dim() != 4:
+        return False
+    sb, sc, sy, sx = t.stride()
+    Cn = t.shape[1]
+    if Cn > 1 and sc != 1:
+        return False
+    return sx >= Cn and sx % 4 == 0 and sy % 4 == 0 and sb % 4 == 0 and t.data_ptr() % 16 == 0
+
+
+def pack_nhwc(t: torch.Tensor) -> torch.Tensor:
+    """(B,C,H,W) fp32, any strides -> contiguous (B,H,W,C) via naf_pack_nhwc_f32."""
+    dev = _require_cuda(t)
+    if t.dtype != torch.float32:
+        t = t.float()
+    B, Cn, H, W = t.shape
+    out = torch.empty((B, H, W, Cn), device=dev, dtype=torch.float32)
+    sb, sc, sy, sx = t.stride()
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_pack_nhwc_f32(_ptr(t), _ptr(out), B, Cn, H, W, sb, sc, sy, sx, _stream(dev))
+    _lib.check(rc, "naf_pack_nhwc_f32")
+    return out
+
+
+def as_pixel_major(t: torch.Tensor) -> torch.Tensor:
+    """NCHW-shaped view whose storage is pixel-major (no copy when it already is)."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    if is_pixel_major(t):
+        return t
+    return pack_nhwc(t).permute(0, 3, 1, 2)
+
+
+# --------------------------------------------------------------------------------- rope tables
+def rope_axis_tables(H: int, W: int, periods: torch.Tensor):
+    """Per-axis cos/sin tables (cos_y, sin_y: (H,P); cos_x, sin_x: (W,P)), P = len(periods).
+
+    Same torch ops, in the same order, as the reference's RoPE (src/layers/rope.py:99-105 for
+    the "separate" coordinates, :139-146 for the angles) so the table entries are bit-identical
+    to the entries of its (H*W, D_head) cos/sin tensors on the same device."""
+    dev, dt = periods.device, periods.dtype
+    cy = 2.0 * (torch.arange(0.5, H, device=dev, dtype=dt) / H) - 1.0
+    cx = 2.0 * (torch.arange(0.5, W, device=dev, dtype=dt) / W) - 1.0
+    ang_y = 2 * math.pi * cy[:, None] / periods[None, :]
+    ang_x = 2 * math.pi * cx[:, None] / periods[None, :]
+    return (torch.cos(ang_y).contiguous(), torch.sin(ang_y).contiguous(),
+            torch.cos(ang_x).contiguous(), torch.sin(ang_x).contiguous())
+
+
+# -------------------------------------------------------------------------- rope + key pooling
+def rope_kpool(x: torch.Tensor, tables, rope_heads: int, pooled_hw=None, want_q: bool = False):
+    """x (B,D,Ho,Wo) -> (k (B,D,h,w) or None, q (B,D,Ho,Wo) or None), both pixel-major views.
+
+    tables = (cos_y, sin_y, cos_x, sin_x) or None (x already rotated)."""
+    dev = _require_cuda(x)
+    x = as_pixel_major(x)
+    B, D, Ho, Wo = x.shape
+    k = q = None
+    h = w = 0
+    if pooled_hw is not None:
+        h, w = int(pooled_hw[0]), int(pooled_hw[1])
+        k = torch.empty((B, h, w, D), device=dev, dtype=torch.float32)
+    if want_q:
+        q = torch.empty((B, Ho, Wo, D), device=dev, dtype=torch.float32)
+    if k is None and q is None:
+        raise ValueError("rope_kpool: nothing to compute")
+    p = _lib.KPoolParams()
+    p.x, p.k_out, p.q_out = _ptr(x), _ptr(k), _ptr(q)
+    if tables is not None:
+        for name, t in zip(("cos_y", "sin_y", "cos_x", "sin_x"), tables):
+            assert t.is_contiguous() and t.dtype == torch.float32 and t.device == dev
+            setattr(p, name, _ptr(t))
+        if tables[0].shape[0] != Ho or tables[2].shape[0] != Wo:
+            raise ValueError("rope tables do not match the map size")
+    p.B, p.D, p.Ho, p.Wo, p.h, p.w = B, D, Ho, Wo, h, w
+    p.rope_heads = int(rope_heads)
+    p.x_stride_b, _, p.x_stride_y, p.x_stride_x = x.stride()
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_rope_kpool_f32(C.byref(p), _stream(dev))
+    _lib.check(rc, "naf_rope_kpool_f32")
+    return (None if k is None else k.permute(0, 3, 1, 2),
+            None if q is None else q.permute(0, 3, 1, 2))
+
+
+# ---------------------------------------------------------------------------------- attention
+_tap_cache: dict = {}
+
+
+def device_tap_tables(Ho, Wo, h, w, K, dev):
+    """int32 device tables (row_tap, col_tap) or (None, None) for integer ratios; cached."""
+    key = (Ho, Wo, h, w, K, str(dev))
+    hit = _tap_cache.get(key)
+    if hit is None:
+        rt, ct = taps.tap_tables(Ho, Wo, h, w, K)
+        if rt is None:
+            hit = (None, None)
+        else:
+            hit = (torch.from_numpy(rt.copy()).to(dev), torch.from_numpy(ct.copy()).to(dev))
+        if len(_tap_cache) > 64:
+            _tap_cache.clear()
+        _tap_cache[key] = hit
+    return hit
+
+
+def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo):
+    B, D, Ho, Wo = q.shape
+    _, Cn, h, w = v.shape
+    p = _lib.XAttnParams()
+    p.q, p.k, p.v, p.out, p.scores = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(scores)
+    p.row_tap, p.col_tap = _ptr(tap_tabs[0]), _ptr(tap_tabs[1])
+    if rope_tabs is not None:
+        p.cos_y, p.sin_y, p.cos_x, p.sin_x = (_ptr(t) for t in rope_tabs)
+    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
+    p.scale = float(scale)
+    p.q_stride_b, _, p.q_stride_y, p.q_stride_x = q.stride()
+    p.algo = int(algo)
+    return p
+
+
+def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_size: int,
+          scale: Optional[float] = None, rope_tables=None, return_scores: bool = False,
+          algo: int = _lib.ALGO_AUTO):
+    """Cross-scale neighbourhood attention.  q (B,D,Ho,Wo), k (B,D,h,w), v (B,C,h,w), all
+    NCHW-shaped; returns out (B,C,Ho,Wo) as a permuted view of pixel-major storage (exactly what
+    the reference returns, src/layers/attentions.py:75) and optionally the scaled pre-softmax
+    scores (B,heads,Ho,Wo,K*K).
+
+    rope_tables: if given, q is the UN-rotated map and RoPE is applied inside the kernel."""
+    dev = _require_cuda(q, k, v)
+    _no_grad_guard(q, k, v)
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError("q, k, v must be 4-D (B, C, H, W)")
+    B, D, Ho, Wo = q.shape
+    if k.shape[0] != B or v.shape[0] != B or k.shape[1] != D or k.shape[-2:] != v.shape[-2:]:
+        raise ValueError(f"inconsistent shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)}")
+    assert D % heads == 0, "dim must be divisible by num_heads"
+    Cn, h, w = v.shape[1:]
+    if Cn % heads != 0:
+        raise ValueError(f"value channels ({Cn}) must be divisible by num_heads ({heads})")
+    K = int(kernel_size)
+    if scale is None:
+        scale = (D // heads) ** -0.5
+    tap_tabs = device_tap_tables(Ho, Wo, h, w, K, dev)  # validates the window too
+    q = as_pixel_major(q)
+    k = as_pixel_major(k)
+    v = as_pixel_major(v)
+    # k and v must be fully contiguous pixel-major
+    if not k.permute(0, 2, 3, 1).is_contiguous():
+        k = pack_nhwc(k).permute(0, 3, 1, 2)
+    if not v.permute(0, 2, 3, 1).is_contiguous():
+        v = pack_nhwc(v).permute(0, 3, 1, 2)
+    out = torch.empty((B, Ho, Wo, Cn), device=dev, dtype=torch.float32)
+    scores = (torch.empty((B, heads, Ho, Wo, K * K), device=dev, dtype=torch.float32)
+              if return_scores else None)
+    p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo)
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_xattn_fwd_f32(C.byref(p), _stream(dev))
+    _lib.check(rc, "naf_xattn_fwd_f32")
+    res = out.permute(0, 3, 1, 2)
+    return (res, scores) if return_scores else res
+
+
+def select_algo(q_shape, v_shape, heads: int, kernel_size: int, rope_on_the_fly: bool = True,
+                return_scores: bool = False) -> str:
+    """Name of the kernel AUTO would pick for these shapes (no launch; dummy aligned pointers)."""
+    B, D, Ho, Wo = q_shape
+    _, Cn, h, w = v_shape
+    K = int(kernel_size)
+    rt, _ = taps.tap_tables(Ho, Wo, h, w, K)
+    p = _lib.XAttnParams()
+    dummy = 1 << 20
+    p.q = p.k = p.v = p.out = dummy
+    if return_scores:
+        p.scores = dummy
+    if rt is not None:
+        p.row_tap = p.col_tap = dummy
+    if rope_on_the_fly:
+        p.cos_y = p.sin_y = p.cos_x = p.sin_x = dummy
+    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
+    p.scale = (D // heads) ** -0.5
+    p.q_stride_b, p.q_stride_y, p.q_stride_x = Ho * Wo * D, Wo * D, D
+    rc = _lib.load().naf_xattn_select_algo(C.byref(p))
+    if rc < 0:
+        _lib.check(-rc, "naf_xattn_select_algo")
+    return _lib.ALGO_NAMES[rc]
+
+
+def dump_taps(Ho: int, Wo: int, h: int, w: int, K: int, dev, force_tables: bool = False) -> torch.Tensor:
+    """(Ho, Wo, K*K) int32 linear low-res indices the kernels gather from (test hook)."""
+    if force_tables:
+        rt = torch.from_numpy(taps.axis_taps(Ho, h, K).copy()).to(dev)
+        ct = torch.from_numpy(taps.axis_taps(Wo, w, K).copy()).to(dev)
+    else:
+        rt, ct = device_tap_tables(Ho, Wo, h, w, K, dev)
+    out = torch.empty((Ho, Wo, K * K), device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_xattn_dump_taps_i32(_ptr(out), _ptr(rt), _ptr(ct), Ho, Wo, h, w, K, _stream(dev))
+    _lib.check(rc, "naf_xattn_dump_taps_i32")
+    return out

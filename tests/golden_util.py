@@ -1,0 +1,52 @@
+"""Load the committed golden fixtures (tests/golden/*.npz, made by oracle/gen_golden.py from the
+unmodified reference modules) and regenerate their seeded inputs."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def seeded_normal(seed, shape):
+    # numpy's legacy MT19937 stream is frozen across numpy versions
+    return torch.from_numpy(np.random.RandomState(int(seed)).standard_normal(tuple(int(s) for s in shape)).astype(np.float32))
+
+
+def names(prefix):
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith(prefix) and f.endswith(".npz")
+                  and not f.endswith("_state.npz"))
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+
+
+def attention_case(name):
+    d = load(name)
+    seed = int(d["seed"])
+    q = seeded_normal(seed, d["q_shape"]) * float(d["gain"])
+    k = seeded_normal(seed + 1, d["k_shape"])
+    v = seeded_normal(seed + 2, d["v_shape"])
+    scores = torch.from_numpy(d["scores"]) if "scores" in d else None
+    return dict(q=q, k=k, v=v, out=torch.from_numpy(d["out"]), scores=scores, heads=int(d["heads"]),
+                K=int(d["kernel_size"]), dilation=tuple(int(x) for x in d["dilation"]))
+
+
+def rope_case(name):
+    d = load(name)
+    return dict(x=seeded_normal(int(d["seed"]), d["x_shape"]), out=torch.from_numpy(d["out"]),
+                periods=torch.from_numpy(d["periods"]), heads=int(d["heads"]))
+
+
+def module_case(name):
+    d = load(name)
+    seed = int(d["seed"])
+    return dict(image=seeded_normal(seed, d["image_shape"]), features=seeded_normal(seed + 1, d["features_shape"]),
+                out=torch.from_numpy(d["out"]), queries=torch.from_numpy(d["queries"]),
+                output_size=tuple(int(x) for x in d["output_size"]))
+
+
+def module_state():
+    d = np.load(os.path.join(GOLDEN, "naf_dim128_k7_state.npz"))
+    return {k: torch.from_numpy(d[k]) for k in d.files}

@@ -1,0 +1,48 @@
+"""CPU: the product's host tap tables (naf_b200/taps.py) are bit-identical to the oracle's and to
+ATen's nearest-exact index map; the closed form used on the device equals the table for every
+integer ratio (all five BASELINE configs included)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from naf_b200 import taps
+from oracle import naf_oracle as O
+
+CONFIG_AXES = [(224, 16, 7), (896, 32, 7), (1036, 37, 11), (1344, 24, 7), (2048, 32, 7), (448, 28, 9)]
+ODD_AXES = [(32, 13, 9), (30, 7, 3), (45, 11, 3), (100, 33, 5), (20, 20, 15), (50, 7, 7), (64, 9, 7), (23, 5, 3)]
+
+
+@pytest.mark.parametrize("out_len,in_len", [(a, b) for a, b, _ in CONFIG_AXES + ODD_AXES] + [(7, 3), (1000, 999), (4096, 37)])
+def test_nearest_exact_matches_aten(out_len, in_len):
+    src = torch.arange(in_len, dtype=torch.float32).view(1, 1, in_len, 1)
+    got = F.interpolate(src, size=(out_len, 1), mode="nearest-exact").view(-1).to(torch.int64).numpy()
+    assert (taps.nearest_exact_source(out_len, in_len) == got).all()
+    assert (O.nearest_exact_index(out_len, in_len) == got).all()
+
+
+@pytest.mark.parametrize("out_len,in_len,K", CONFIG_AXES + ODD_AXES)
+def test_axis_taps_bit_exact_vs_oracle(out_len, in_len, K):
+    a = taps.axis_taps(out_len, in_len, K)
+    b = O.axis_tap_table(out_len, in_len, K)
+    assert a.dtype == np.int32 and a.shape == (out_len, K)
+    assert (a == b).all()
+    assert a.min() >= 0 and a.max() < in_len
+
+
+@pytest.mark.parametrize("out_len,in_len,K", CONFIG_AXES + [(36, 9, 7), (36, 12, 11), (14, 7, 7), (20, 20, 15), (24, 8, 5)])
+def test_closed_form_equals_table_for_integer_ratios(out_len, in_len, K):
+    assert taps.integer_ratio(out_len, in_len)
+    assert (taps.closed_form_axis_taps(out_len, in_len, K) == taps.axis_taps(out_len, in_len, K)).all()
+
+
+def test_tap_tables_none_for_integer_ratios():
+    assert taps.tap_tables(896, 896, 32, 32, 7) == (None, None)
+    rt, ct = taps.tap_tables(32, 48, 13, 16, 9)
+    assert rt.shape == (32, 9) and ct.shape == (48, 9)
+
+
+@pytest.mark.parametrize("args", [(36, 9, 4), (36, 9, 0), (20, 7, 11), (5, 9, 3)])
+def test_invalid_windows_raise(args):
+    with pytest.raises(ValueError):
+        taps.axis_taps(*args)
