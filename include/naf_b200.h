@@ -64,6 +64,13 @@ NAF_API int naf_pack_nhwc_f32(const float* src, float* dst, int B, int C, int H,
                       int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w,
                       void* stream);
 
+/* Same, writing the C channels as the slab [dst_channel_offset, dst_channel_offset + C) of a
+ * pixel-major tensor with dst_channels channels per pixel.  Two calls concatenate the two encoder
+ * branches (reference src/model/naf.py:33, torch.cat) while packing them. */
+NAF_API int naf_pack_nhwc_slab_f32(const float* src, float* dst, int B, int C, int H, int W,
+                      int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w,
+                      int dst_channels, int dst_channel_offset, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * RoPE + key pooling pre-pass.
  *   q      = RoPE(x)                      reference src/layers/rope.py:155-174 (eval branch)
@@ -74,6 +81,12 @@ NAF_API int naf_pack_nhwc_f32(const float* src, float* dst, int B, int C, int H,
  * q_out may be NULL (keys only); when given it receives the rotated map, contiguous
  * (B,Ho,Wo,D).  If all four tables are NULL, x is taken as already rotated.
  * Pooling bins follow ATen: rows [floor(i*Ho/h), ceil((i+1)*Ho/h)).
+ *
+ * Replicated guidance (rep_y, rep_x >= 1): when the conv encoder ran at a resolution (Ho/rep_y,
+ * Wo/rep_x) below the target, the reference's adaptive_avg_pool2d to the target size
+ * (src/model/naf.py:34) is pure replication; x then holds the SOURCE map (B, Ho/rep_y,
+ * Wo/rep_x, D) and target pixel (y, x) reads source pixel (y/rep_y, x/rep_x).  RoPE always uses
+ * the target coordinates.  The strides describe the source map.
  * ---------------------------------------------------------------------------------------- */
 typedef struct naf_kpool_params {
   const float* x;        /* (B,Ho,Wo,D) */
@@ -86,6 +99,7 @@ typedef struct naf_kpool_params {
   int32_t B, D, Ho, Wo, h, w;
   int32_t rope_heads;    /* D % (4*rope_heads) == 0 */
   int64_t x_stride_b, x_stride_y, x_stride_x; /* elements */
+  int32_t rep_y, rep_x;  /* replication factors of x (1 = x is at target resolution) */
 } naf_kpool_params;
 
 NAF_API int naf_rope_kpool_f32(const naf_kpool_params* p, void* stream);
@@ -123,6 +137,7 @@ typedef struct naf_xattn_params {
   float scale;           /* (D/heads)^-0.5 in the reference (src/layers/attentions.py:46) */
   int64_t q_stride_b, q_stride_y, q_stride_x; /* elements */
   int32_t algo;          /* NAF_ALGO_* ; AUTO picks the fastest kernel that supports the request */
+  int32_t rep_y, rep_x;  /* q is a replicated source map (B,Ho/rep_y,Wo/rep_x,D); see kpool */
 } naf_xattn_params;
 
 enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2, NAF_ALGO_CELL_TC = 3 };

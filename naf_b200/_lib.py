@@ -30,7 +30,12 @@ class KPoolParams(C.Structure):
         ("B", C.c_int32), ("D", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
         ("h", C.c_int32), ("w", C.c_int32), ("rope_heads", C.c_int32),
         ("x_stride_b", C.c_int64), ("x_stride_y", C.c_int64), ("x_stride_x", C.c_int64),
+        ("rep_y", C.c_int32), ("rep_x", C.c_int32),
     ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.rep_y = self.rep_x = 1
 
 
 class XAttnParams(C.Structure):
@@ -44,8 +49,12 @@ class XAttnParams(C.Structure):
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("K", C.c_int32),
         ("scale", C.c_float),
         ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
-        ("algo", C.c_int32),
+        ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32),
     ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.rep_y = self.rep_x = 1
 
 
 #: every symbol include/naf_b200.h declares: name -> (restype, argtypes)
@@ -55,6 +64,8 @@ EXPORTS = {
     "naf_has_tensor_path": (C.c_int, []),
     "naf_pack_nhwc_f32": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int64, C.c_int64, C.c_int64, C.c_int64, _fp]),
+    "naf_pack_nhwc_slab_f32": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, _fp]),
     "naf_rope_kpool_f32": (C.c_int, [C.POINTER(KPoolParams), _fp]),
     "naf_xattn_fwd_f32": (C.c_int, [C.POINTER(XAttnParams), _fp]),
     "naf_xattn_select_algo": (C.c_int, [C.POINTER(XAttnParams)]),

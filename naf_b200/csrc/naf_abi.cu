@@ -59,6 +59,9 @@ static int validate_xattn(const naf_xattn_params& p) {
                 "xattn: on-the-fly RoPE needs head dim %% 4 == 0");
   NAF_REQUIRE(p.q_stride_x >= p.D && p.q_stride_y >= 0 && p.q_stride_b >= 0, NAF_ERR_BAD_SHAPE,
               "xattn: bad q strides");
+  NAF_REQUIRE(p.rep_y >= 1 && p.rep_x >= 1 && p.Ho % p.rep_y == 0 && p.Wo % p.rep_x == 0,
+              NAF_ERR_BAD_SHAPE, "xattn: replication factors (%d,%d) must divide the target size",
+              p.rep_y, p.rep_x);
   return NAF_OK;
 }
 
@@ -102,8 +105,20 @@ int naf_pack_nhwc_f32(const float* src, float* dst, int B, int C, int H, int W, 
                       int64_t stride_c, int64_t stride_h, int64_t stride_w, void* stream) {
   NAF_REQUIRE(src && dst, NAF_ERR_NULL, "pack_nhwc: NULL pointer");
   NAF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "pack_nhwc: sizes must be positive");
-  return launch_pack_nhwc(src, dst, B, C, H, W, stride_b, stride_c, stride_h, stride_w,
+  return launch_pack_nhwc(src, dst, B, C, H, W, stride_b, stride_c, stride_h, stride_w, C, 0,
                           static_cast<cudaStream_t>(stream));
+}
+
+int naf_pack_nhwc_slab_f32(const float* src, float* dst, int B, int C, int H, int W,
+                           int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w,
+                           int dst_channels, int dst_channel_offset, void* stream) {
+  NAF_REQUIRE(src && dst, NAF_ERR_NULL, "pack_nhwc_slab: NULL pointer");
+  NAF_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "pack_nhwc_slab: sizes must be positive");
+  NAF_REQUIRE(dst_channel_offset >= 0 && dst_channel_offset + C <= dst_channels, NAF_ERR_BAD_SHAPE,
+              "pack_nhwc_slab: slab [%d, %d) does not fit %d channels", dst_channel_offset,
+              dst_channel_offset + C, dst_channels);
+  return launch_pack_nhwc(src, dst, B, C, H, W, stride_b, stride_c, stride_h, stride_w,
+                          dst_channels, dst_channel_offset, static_cast<cudaStream_t>(stream));
 }
 
 int naf_rope_kpool_f32(const naf_kpool_params* pp, void* stream) {
@@ -121,6 +136,9 @@ int naf_rope_kpool_f32(const naf_kpool_params* pp, void* stream) {
     NAF_REQUIRE(p.rope_heads > 0 && p.D % (4 * p.rope_heads) == 0, NAF_ERR_BAD_SHAPE,
                 "rope_kpool: embed_dim %% (4*num_heads) must be 0");
   NAF_REQUIRE(p.x_stride_x >= p.D, NAF_ERR_BAD_SHAPE, "rope_kpool: bad x strides");
+  NAF_REQUIRE(p.rep_y >= 1 && p.rep_x >= 1 && p.Ho % p.rep_y == 0 && p.Wo % p.rep_x == 0,
+              NAF_ERR_BAD_SHAPE, "rope_kpool: replication factors (%d,%d) must divide the map size",
+              p.rep_y, p.rep_x);
   return launch_rope_kpool(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -88,7 +88,8 @@ __device__ __forceinline__ void stg_stream2(float* p, const float2 v) {
 
 // ---- kernel launchers implemented in the individual .cu files --------------------------------
 int launch_pack_nhwc(const float* src, float* dst, int B, int C, int H, int W, int64_t sb,
-                     int64_t sc, int64_t sh, int64_t sw, cudaStream_t st);
+                     int64_t sc, int64_t sh, int64_t sw, int dst_channels, int dst_offset,
+                     cudaStream_t st);
 int launch_rope_kpool(const naf_kpool_params& p, cudaStream_t st);
 int launch_xattn_generic(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why);

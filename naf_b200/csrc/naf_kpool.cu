@@ -84,7 +84,7 @@ rope_kpool_kernel(naf_kpool_params p, int lanes, int groups, int bins_h, int bin
     for (int pi = group; pi < npix; pi += groups) {
       const int yy = ys + pi / bw;
       const int xx = xs + pi % bw;
-      const float* px = xb + int64_t(yy) * p.x_stride_y + int64_t(xx) * p.x_stride_x;
+      const float* px = xb + int64_t(yy / p.rep_y) * p.x_stride_y + int64_t(xx / p.rep_x) * p.x_stride_x;
       float a[VEC], bb[VEC];
       load_vec_stream<VEC>(a, px + ca);
       load_vec_stream<VEC>(bb, px + ca + half);

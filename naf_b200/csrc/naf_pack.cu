@@ -7,7 +7,7 @@ namespace naf {
 // run along channels (the contiguous axis of the packed layout).  Both sides are 128 B coalesced.
 __global__ void __launch_bounds__(256)
 pack_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int H, int W,
-                 int64_t sb, int64_t sc, int64_t sh, int64_t sw) {
+                 int64_t sb, int64_t sc, int64_t sh, int64_t sw, int dstC, int dst_off) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int c0 = blockIdx.y * 32;
@@ -32,18 +32,18 @@ pack_nhwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, 
   for (int i = 0; i < 4; ++i) {
     const int64_t pp = p0 + ty + 8 * i;
     const int c = c0 + tx;
-    if (c < C && pp < HW) dst[(int64_t(b) * HW + pp) * C + c] = tile[tx][ty + 8 * i];
+    if (c < C && pp < HW) dst[(int64_t(b) * HW + pp) * dstC + dst_off + c] = tile[tx][ty + 8 * i];
   }
 }
 
 int launch_pack_nhwc(const float* src, float* dst, int B, int C, int H, int W, int64_t sb,
-                     int64_t sc, int64_t sh, int64_t sw, cudaStream_t st) {
+                     int64_t sc, int64_t sh, int64_t sw, int dstC, int dst_off, cudaStream_t st) {
   const int64_t HW = int64_t(H) * W;
   const int64_t ptiles = (HW + 31) / 32;
   NAF_REQUIRE(ptiles < (int64_t(1) << 31) && B <= 65535 && (C + 31) / 32 <= 65535,
               NAF_ERR_UNSUPPORTED, "pack_nhwc: tensor too large for one launch");
   dim3 grid(unsigned(ptiles), unsigned((C + 31) / 32), unsigned(B));
-  pack_nhwc_kernel<<<grid, 256, 0, st>>>(src, dst, C, H, W, sb, sc, sh, sw);
+  pack_nhwc_kernel<<<grid, 256, 0, st>>>(src, dst, C, H, W, sb, sc, sh, sw, dstC, dst_off);
   return check_launch("pack_nhwc");
 }
 

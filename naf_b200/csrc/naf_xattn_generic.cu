@@ -34,8 +34,8 @@ xattn_generic_kernel(naf_xattn_params p, int rh, int rw, int64_t total_items) {
     const int y = int(pix % p.Ho);
     const int b = int(pix / p.Ho);
 
-    const float* qp = p.q + int64_t(b) * p.q_stride_b + int64_t(y) * p.q_stride_y +
-                      int64_t(x) * p.q_stride_x + head * dq;
+    const float* qp = p.q + int64_t(b) * p.q_stride_b + int64_t(y / p.rep_y) * p.q_stride_y +
+                      int64_t(x / p.rep_x) * p.q_stride_x + head * dq;
     if (rope) {
       for (int i = lane; i < half; i += 32) {
         const float a = qp[i], bb = qp[i + half];

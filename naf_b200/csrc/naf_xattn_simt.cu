@@ -95,7 +95,7 @@ xattn_cell_simt_kernel(naf_xattn_params p, int rh, int rw, int dv) {
       if (pi >= npix) pi = npix - 1;  // duplicate the last pixel; its stores are masked later
       const int py = pi / rw;
       const int y = y0 + py, x = x0 + (pi - py * rw);
-      const float* qp = qbase + int64_t(y) * p.q_stride_y + int64_t(x) * p.q_stride_x;
+      const float* qp = qbase + int64_t(y / p.rep_y) * p.q_stride_y + int64_t(x / p.rep_x) * p.q_stride_x;
       float2 q[DQ / 2];
 #pragma unroll
       for (int i = 0; i < DQ / 4; ++i) {

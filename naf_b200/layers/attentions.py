@@ -32,10 +32,10 @@ class CrossAttention(nn.Module):
             return int(ks[0])
         return int(ks)
 
-    def forward(self, q, k, v, image=None, return_weights=False, rope_tables=None, **kwargs):
-        hq, wq = q.shape[-2:]
+    def forward(self, q, k, v, image=None, return_weights=False, rope_tables=None, rep=(1, 1), **kwargs):
+        hq, wq = q.shape[-2] * int(rep[0]), q.shape[-1] * int(rep[1])
         hk, wk = k.shape[-2:]
         self.dilation = (hq // hk, wq // wk)
         res = ops.xattn(q, k, v, self.num_heads, self._square_kernel(), scale=self.scale,
-                        rope_tables=rope_tables, return_scores=return_weights, algo=self.algo)
+                        rope_tables=rope_tables, return_scores=return_weights, algo=self.algo, rep=rep)
         return res

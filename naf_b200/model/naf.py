@@ -45,21 +45,38 @@ class ImageEncoder(nn.Module):
         return Hi, Wi
 
     def forward_encoder(self, x, output_size):
-        if x.is_cuda:
-            x = x.contiguous(memory_format=torch.channels_last)
         if self.use_encoder:
             x = torch.cat([self.encoder(x), self.sem_encoder(x)], dim=1)
         if tuple(x.shape[-2:]) != tuple(int(s) for s in output_size):
             x = F.adaptive_avg_pool2d(x, output_size=output_size)  # identity when sizes match
         return x
 
-    def guidance(self, image, output_size):
-        """Pooled, UN-rotated guidance map (B, D, Ho, Wo)."""
-        Ho, Wo = int(output_size[0]), int(output_size[1])
+    def _capped(self, image, Ho, Wo):
         size = self.encoder_resolution(image.shape[-2:], (Ho, Wo))
         if size != tuple(image.shape[-2:]):
             image = F.interpolate(image, size=size, mode="bilinear", align_corners=False)
-        return self.forward_encoder(image, (Ho, Wo))
+        return image
+
+    def guidance(self, image, output_size):
+        """Pooled, UN-rotated guidance map (B, D, Ho, Wo) -- the reference's tensor, materialised."""
+        Ho, Wo = int(output_size[0]), int(output_size[1])
+        return self.forward_encoder(self._capped(image, Ho, Wo), (Ho, Wo))
+
+    def guidance_source(self, image, output_size):
+        """(x_src, (ry, rx)): the pooled guidance map WITHOUT materialising replication.
+
+        When the target size is an integer multiple of the encoder resolution (equal sizes
+        included) the reference's `adaptive_avg_pool2d` (src/model/naf.py:34) only replicates
+        pixels, so the kernels read the encoder-resolution map through `rep` instead; the two
+        branch outputs are concatenated and packed pixel-major by our packing kernel in the same
+        pass.  Otherwise this falls back to the materialised `guidance()` with rep (1, 1)."""
+        Ho, Wo = int(output_size[0]), int(output_size[1])
+        image = self._capped(image, Ho, Wo)
+        Hs, Ws = image.shape[-2:]
+        if not (image.is_cuda and self.use_encoder and Ho % Hs == 0 and Wo % Ws == 0):
+            return self.forward_encoder(image, (Ho, Wo)), (1, 1)
+        parts = [self.encoder(image), self.sem_encoder(image)]
+        return ops.pack_concat_nhwc(parts), (Ho // Hs, Wo // Ws)
 
     def forward(self, x, output_size):
         return self.rope(self.guidance(x, output_size))
@@ -90,18 +107,20 @@ class NAF(nn.Module):
         self.upsampler = CrossAttention(dim=dim, num_heads=heads_attn,
                                         kernel_size=(kernel_size, kernel_size))
 
-    def upsample_from_guidance(self, x, features, return_weights=False):
-        """The hot path proper: pooled un-rotated guidance x (B,D,Ho,Wo) + features (B,C,h,w)
-        -> (B,C,Ho,Wo).  Two kernel launches (+ one tiny packing launch for V)."""
+    def upsample_from_guidance(self, x, features, return_weights=False, rep=(1, 1)):
+        """The hot path proper: pooled un-rotated guidance x (B,D,Ho/ry,Wo/rx) + features
+        (B,C,h,w) -> (B,C,Ho,Wo).  Two kernel launches (+ one tiny packing launch for V)."""
         rope = self.image_encoder.rope
-        Ho, Wo = x.shape[-2:]
+        Ho, Wo = x.shape[-2] * rep[0], x.shape[-1] * rep[1]
         tables = rope.axis_tables(Ho, Wo)
         D = x.shape[1]
+        x = ops.as_pixel_major(x)  # once, shared by both kernels
         fused = rope.D_head == D // self.upsampler.num_heads
         k, q = ops.rope_kpool(x, tables, rope.num_heads, pooled_hw=features.shape[-2:],
-                              want_q=not fused)
+                              want_q=not fused, rep=rep)
         if fused:
-            return self.upsampler(x, k, features, return_weights=return_weights, rope_tables=tables)
+            return self.upsampler(x, k, features, return_weights=return_weights, rope_tables=tables,
+                                  rep=rep)
         return self.upsampler(q, k, features, return_weights=return_weights)
 
     def forward(self, image, features, output_size, return_weights=False, *args, **kwargs):
@@ -110,5 +129,5 @@ class NAF(nn.Module):
             if torch.is_grad_enabled() and self.training:
                 raise RuntimeError("naf_b200.NAF is forward-only: use torch.no_grad() and .eval()")
         with torch.no_grad():
-            x = self.image_encoder.guidance(image, output_size)
-            return self.upsample_from_guidance(x, features, return_weights=return_weights)
+            x, rep = self.image_encoder.guidance_source(image, output_size)
+            return self.upsample_from_guidance(x, features, return_weights=return_weights, rep=rep)

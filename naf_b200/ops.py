@@ -17,6 +17,18 @@ import torch
 from . import _lib, taps
 
 
+# ------------------------------------------------------------------------------ instrumentation
+#: number of kernels of OURS launched through the C ABI since import (bench.py reports the delta)
+LAUNCHES = {"pack_nhwc": 0, "rope_kpool": 0, "xattn": 0}
+#: when set to a list, xattn() appends a (start, end) CUDA-event pair around its kernel launch,
+#: recorded on the stream the kernel is launched on (bench.py's live roofline measurement)
+XATTN_EVENTS = None
+
+
+def launch_count() -> int:
+    return sum(LAUNCHES.values())
+
+
 # ------------------------------------------------------------------------------------ helpers
 def _require_cuda(*tensors: torch.Tensor) -> torch.device:
     dev = None
@@ -71,7 +83,32 @@ def pack_nhwc(t: torch.Tensor) -> torch.Tensor:
     with torch.cuda.device(dev):
         rc = _lib.load().naf_pack_nhwc_f32(_ptr(t), _ptr(out), B, Cn, H, W, sb, sc, sy, sx, _stream(dev))
     _lib.check(rc, "naf_pack_nhwc_f32")
+    LAUNCHES["pack_nhwc"] += 1
     return out
+
+
+def pack_concat_nhwc(parts) -> torch.Tensor:
+    """torch.cat(parts, dim=1) + pixel-major packing in one pass per part (naf_pack_nhwc_slab_f32):
+    parts are (B,Ci,H,W) fp32 tensors of any strides; returns the NCHW-shaped pixel-major view of
+    a contiguous (B,H,W,sum Ci) buffer."""
+    dev = _require_cuda(*parts)
+    B, _, H, W = parts[0].shape
+    total = sum(int(t.shape[1]) for t in parts)
+    out = torch.empty((B, H, W, total), device=dev, dtype=torch.float32)
+    off = 0
+    with torch.cuda.device(dev):
+        for t in parts:
+            if t.dtype != torch.float32:
+                t = t.float()
+            if tuple(t.shape[0:1] + t.shape[2:]) != (B, H, W):
+                raise ValueError("pack_concat_nhwc: parts disagree on (B, H, W)")
+            sb, sc, sy, sx = t.stride()
+            rc = _lib.load().naf_pack_nhwc_slab_f32(_ptr(t), _ptr(out), B, t.shape[1], H, W, sb, sc, sy, sx,
+                                                    total, off, _stream(dev))
+            _lib.check(rc, "naf_pack_nhwc_slab_f32")
+            LAUNCHES["pack_nhwc"] += 1
+            off += int(t.shape[1])
+    return out.permute(0, 3, 1, 2)
 
 
 def as_pixel_major(t: torch.Tensor) -> torch.Tensor:
@@ -100,13 +137,17 @@ def rope_axis_tables(H: int, W: int, periods: torch.Tensor):
 
 
 # -------------------------------------------------------------------------- rope + key pooling
-def rope_kpool(x: torch.Tensor, tables, rope_heads: int, pooled_hw=None, want_q: bool = False):
+def rope_kpool(x: torch.Tensor, tables, rope_heads: int, pooled_hw=None, want_q: bool = False,
+               rep=(1, 1)):
     """x (B,D,Ho,Wo) -> (k (B,D,h,w) or None, q (B,D,Ho,Wo) or None), both pixel-major views.
 
-    tables = (cos_y, sin_y, cos_x, sin_x) or None (x already rotated)."""
+    tables = (cos_y, sin_y, cos_x, sin_x) or None (x already rotated).
+    rep = (ry, rx): x is a SOURCE map (B,D,Ho/ry,Wo/rx) each pixel of which stands for an
+    ry x rx block of target pixels (the reference's adaptive_avg_pool2d up-replication)."""
     dev = _require_cuda(x)
     x = as_pixel_major(x)
     B, D, Ho, Wo = x.shape
+    Ho, Wo = Ho * int(rep[0]), Wo * int(rep[1])
     k = q = None
     h = w = 0
     if pooled_hw is not None:
@@ -127,9 +168,11 @@ def rope_kpool(x: torch.Tensor, tables, rope_heads: int, pooled_hw=None, want_q:
     p.B, p.D, p.Ho, p.Wo, p.h, p.w = B, D, Ho, Wo, h, w
     p.rope_heads = int(rope_heads)
     p.x_stride_b, _, p.x_stride_y, p.x_stride_x = x.stride()
+    p.rep_y, p.rep_x = int(rep[0]), int(rep[1])
     with torch.cuda.device(dev):
         rc = _lib.load().naf_rope_kpool_f32(C.byref(p), _stream(dev))
     _lib.check(rc, "naf_rope_kpool_f32")
+    LAUNCHES["rope_kpool"] += 1
     return (None if k is None else k.permute(0, 3, 1, 2),
             None if q is None else q.permute(0, 3, 1, 2))
 
@@ -154,8 +197,9 @@ def device_tap_tables(Ho, Wo, h, w, K, dev):
     return hit
 
 
-def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo):
+def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo, rep=(1, 1)):
     B, D, Ho, Wo = q.shape
+    Ho, Wo = Ho * int(rep[0]), Wo * int(rep[1])
     _, Cn, h, w = v.shape
     p = _lib.XAttnParams()
     p.q, p.k, p.v, p.out, p.scores = _ptr(q), _ptr(k), _ptr(v), _ptr(out), _ptr(scores)
@@ -166,23 +210,26 @@ def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo
     p.scale = float(scale)
     p.q_stride_b, _, p.q_stride_y, p.q_stride_x = q.stride()
     p.algo = int(algo)
+    p.rep_y, p.rep_x = int(rep[0]), int(rep[1])
     return p
 
 
 def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_size: int,
           scale: Optional[float] = None, rope_tables=None, return_scores: bool = False,
-          algo: int = _lib.ALGO_AUTO):
+          algo: int = _lib.ALGO_AUTO, rep=(1, 1)):
     """Cross-scale neighbourhood attention.  q (B,D,Ho,Wo), k (B,D,h,w), v (B,C,h,w), all
     NCHW-shaped; returns out (B,C,Ho,Wo) as a permuted view of pixel-major storage (exactly what
     the reference returns, src/layers/attentions.py:75) and optionally the scaled pre-softmax
     scores (B,heads,Ho,Wo,K*K).
 
-    rope_tables: if given, q is the UN-rotated map and RoPE is applied inside the kernel."""
+    rope_tables: if given, q is the UN-rotated map and RoPE is applied inside the kernel.
+    rep: q is a replicated source map (see rope_kpool); the target size is q's size times rep."""
     dev = _require_cuda(q, k, v)
     _no_grad_guard(q, k, v)
     if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
         raise ValueError("q, k, v must be 4-D (B, C, H, W)")
     B, D, Ho, Wo = q.shape
+    Ho, Wo = Ho * int(rep[0]), Wo * int(rep[1])
     if k.shape[0] != B or v.shape[0] != B or k.shape[1] != D or k.shape[-2:] != v.shape[-2:]:
         raise ValueError(f"inconsistent shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)}")
     assert D % heads == 0, "dim must be divisible by num_heads"
@@ -204,10 +251,18 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_
     out = torch.empty((B, Ho, Wo, Cn), device=dev, dtype=torch.float32)
     scores = (torch.empty((B, heads, Ho, Wo, K * K), device=dev, dtype=torch.float32)
               if return_scores else None)
-    p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo)
+    p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo, rep)
     with torch.cuda.device(dev):
+        ev = None
+        if XATTN_EVENTS is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream(dev))
         rc = _lib.load().naf_xattn_fwd_f32(C.byref(p), _stream(dev))
+        if ev is not None:
+            ev[1].record(torch.cuda.current_stream(dev))
+            XATTN_EVENTS.append(ev)
     _lib.check(rc, "naf_xattn_fwd_f32")
+    LAUNCHES["xattn"] += 1
     res = out.permute(0, 3, 1, 2)
     return (res, scores) if return_scores else res
 
