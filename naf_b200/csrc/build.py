@@ -39,7 +39,7 @@ def command(verbose: bool = False) -> list[str]:
     cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "-shared",
-           "-I", os.path.join(ROOT, "include"), "-I", HERE, "-DNAF_BUILDING_LIB",
+           "-I", os.path.join(ROOT, "include"), "-I", HERE, "-DNAF_BUILDING_LIB", "-DNAF_WITH_TC",
            "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
