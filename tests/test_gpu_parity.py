@@ -171,7 +171,7 @@ def test_fused_rope_path_matches_oracle(case):
 def test_replicated_guidance_source(rep):
     """Kernels reading the encoder-resolution map through `rep` == oracle on the replicated map
     (what the reference's adaptive_avg_pool2d produces when the target is a multiple)."""
-    B, D, Cv, Hs, Ws, K = 2, 256, 128, 28, 42, 3
+    B, D, Cv, Hs, Ws, K = 2, 256, 128, 42, 56, 3
     Ho, Wo = Hs * rep[0], Ws * rep[1]
     h, w = Ho // 14, Wo // 14
     xs, feats = rnd(7, B, D, Hs, Ws), rnd(8, B, Cv, h, w)
