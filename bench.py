@@ -43,6 +43,15 @@ WORKLOADS = {
 D_GUIDE = 256
 
 
+def ncu_traffic(kernel, workload):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return int(json.load(fh)[f"{kernel}:{workload}"]["bytes"])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -321,7 +330,8 @@ def main():
                         "result sample: the upsampled features at every cell centre (B,C,h,w)")},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"xattn ({chosen})", "achieved": round(achieved, 1),
-                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                     "traffic": ncu_traffic(chosen, args.workload),
                      "kernel_ms": round(xattn_ms, 4), "algorithmic_bytes": int(algo_bytes),
                      "peak_source": peak_src},
         "clocks": clocks,

@@ -84,13 +84,13 @@ __device__ __forceinline__ void stg_stream(float* p, const float4 v) {
 }
 // 256-bit (sm_100+) streaming global load / store: one full 32-byte sector per thread
 __device__ __forceinline__ void ldg_stream8(const float* p, float (&r)[8]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]),
                  "=f"(r[7])
                : "l"(p));
 }
 __device__ __forceinline__ void ldg8(const float* p, float (&r)[8]) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+  asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]),
                  "=f"(r[7])
                : "l"(p));
@@ -99,6 +99,9 @@ __device__ __forceinline__ void stg_stream8(float* p, const float (&r)[8]) {
   asm volatile("st.global.cs.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]),
                "f"(r[2]), "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
                : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 __device__ __forceinline__ void stg_stream2(float* p, const float2 v) {

@@ -25,6 +25,10 @@
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
+#ifndef NAF_TC_EXP
+#define NAF_TC_EXP 0   // profiling experiments only (scripts/tc_experiments.sh); 0 in every real build
+#endif
+
 namespace naf {
 
 using namespace umma;
@@ -34,6 +38,10 @@ namespace {
 constexpr int DQ = 64;        // query/key head dim this kernel is specialised for
 constexpr int KC = DQ / 8;    // 16-byte chunks along the head dim
 constexpr int NT = 256;       // threads per CTA
+
+// window side <-> padded tap count is one-to-one for the supported kernels (3,5,7,9,11)
+template <int TP>
+struct WindowOf { static constexpr int K = TP == 16 ? 3 : TP == 32 ? 5 : TP == 64 ? 7 : TP == 96 ? 9 : 11; };
 
 template <int TP, int DV>
 struct TcCfg {
@@ -77,7 +85,7 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
   const int half = warp >> 2;       // which half of the columns this thread owns
   const int row = rowgrp * 32 + lane;
 
-  const int K = p.K, K2 = K * K;
+  constexpr int K = WindowOf<TP>::K, K2 = K * K;
   int bid = blockIdx.x;
   const int head = bid % p.heads;
   bid /= p.heads;
@@ -96,6 +104,7 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
   }
 
   // ---- stage the K window: canonical K-major [chunk c][tap n][16 B], zero rows for n >= K2
+#pragma unroll 2
   for (int i = tid; i < TP * KC; i += NT) {
     const int n = i % TP, c = i / TP;
     uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
@@ -112,6 +121,7 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
   // ---- stage the V window: canonical MN-major [tap group][channel group][tap%8][16 B]
   {
     constexpr int NG = DV / 8;
+#pragma unroll 4
     for (int i = tid; i < TP * NG; i += NT) {
       const int kk = i & 7;
       const int g = (i >> 3) % NG;
@@ -141,25 +151,36 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
   const float* qbase = p.q + int64_t(b) * p.q_stride_b + head * DQ + P * half;
   float* obase = p.out + int64_t(b) * p.Ho * p.Wo * p.C + head * DV;
 
-  float qa[P], qb[P];
+  float qa[P], qb[P];   // raw (un-rotated) prefetched q of the NEXT tile, then rotated in place
   int64_t my_pix = -1;  // linear target pixel of this thread's row, or -1
+  int my_y = 0, my_x = 0;
 
-  auto load_q = [&](int tile) {
+  // issue the q loads of `tile` (no consumer: the latency overlaps the current tile's work)
+  auto issue_q = [&](int tile) {
     int pi = tile * 128 + row;
     const bool valid = pi < npix;
     if (!valid) pi = npix - 1;
     const int py = pi / rw;
-    const int y = y0 + py, x = x0 + (pi - py * rw);
-    my_pix = valid ? int64_t(y) * p.Wo + x : -1;
-    const float* qp = qbase + int64_t(y / p.rep_y) * p.q_stride_y + int64_t(x / p.rep_x) * p.q_stride_x;
+    my_y = y0 + py;
+    my_x = x0 + (pi - py * rw);
+    my_pix = valid ? int64_t(my_y) * p.Wo + my_x : -1;
+    const float* qp = qbase + int64_t(my_y / p.rep_y) * p.q_stride_y + int64_t(my_x / p.rep_x) * p.q_stride_x;
+#if NAF_TC_EXP & 2
+    for (int j = 0; j < P; ++j) { qa[j] = float(j + tile) * 0.01f; qb[j] = float(j - row) * 0.02f; }
+    (void)qp;
+#else
     ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
     ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
     ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
     ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+#endif
+  };
+  // rotate + scale the prefetched q in place (tables are L1/L2 resident)
+  auto finish_q = [&]() {
     if (rope) {
       // half 0 rotates by the row angles, half 1 by the column angles (src/layers/rope.py:139-143)
-      const float* ct = half == 0 ? p.cos_y + int64_t(y) * P : p.cos_x + int64_t(x) * P;
-      const float* st = half == 0 ? p.sin_y + int64_t(y) * P : p.sin_x + int64_t(x) * P;
+      const float* ct = half == 0 ? p.cos_y + int64_t(my_y) * P : p.cos_x + int64_t(my_x) * P;
+      const float* st = half == 0 ? p.sin_y + int64_t(my_y) * P : p.sin_x + int64_t(my_x) * P;
       float c[P], s[P];
       ldg8(ct, *reinterpret_cast<float(*)[8]>(&c[0]));
       ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
@@ -180,7 +201,7 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
     }
   };
 
-  load_q(0);
+  issue_q(0);
 
   // wait for the TMEM base address and make barrier inits visible
   fence_before_sync();
@@ -198,6 +219,8 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
   for (int tile = 0; tile < ntiles; ++tile) {
     // ================= stage Q: canonical K-major [chunk][row][16 B]; this thread owns chunks
     // 2h, 2h+1 (a part) and 4+2h, 4+2h+1 (b part)
+    finish_q();
+    const int64_t cur_pix = my_pix;
     {
       uint4 hi, lo;
       split8(&qa[0], hi, lo);
@@ -213,7 +236,6 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
       *reinterpret_cast<uint4*>(sQhi + ((5 + 2 * half) * 128 + row) * 16) = hi;
       *reinterpret_cast<uint4*>(sQlo + ((5 + 2 * half) * 128 + row) * 16) = lo;
     }
-    const int64_t cur_pix = my_pix;
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -228,13 +250,15 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
         for (int kk = 0; kk < DQ / 16; ++kk) {
           const uint64_t da = make_desc(a0 + kk * 2 * (128 * 16), 128 * 16, 128);
           const uint64_t db = make_desc(b0 + kk * 2 * (TP * 16), TP * 16, 128);
+#if !(NAF_TC_EXP & 4)
           mma_f16_ss(tS, da, db, idesc_qk, (pass | kk) != 0);
+#endif
         }
       }
       commit(&mbar[0]);
     }
     // ================= prefetch the next tile's q while the tensor core works
-    if (tile + 1 < ntiles) load_q(tile + 1);
+    if (tile + 1 < ntiles) issue_q(tile + 1);
 
     mbar_wait(&mbar[0], phase);
     fence_after_sync();
@@ -304,7 +328,9 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
 #pragma unroll
         for (int kk = 0; kk < TP / 16; ++kk) {
           const uint64_t db = make_desc(b0 + kk * 2 * (DV / 8) * 128, (DV / 8) * 128, 128);
+#if !(NAF_TC_EXP & 4)
           mma_f16_ts(tO, a0 + kk * 8, db, idesc_pv, (pass | kk) != 0);
+#endif
         }
       }
       commit(&mbar[1]);
@@ -317,22 +343,32 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
     // 256-bit streaming stores (chunks c with c % 2 == half)
     {
       float* orow = obase + cur_pix * p.C;
+      constexpr int NCH = DV / 32;                       // 32-column chunks of the O row
+      const int nmine = (NCH + 1 - half) / 2;            // chunks half, half+2, ...
+      uint32_t r[2][32];
+      if (nmine > 0) tmem_ld32(tO + lane_off + half * 32, r[0]);
 #pragma unroll
-      for (int c = 0; c < DV / 32; ++c) {
-        if ((c & 1) != half) continue;
-        uint32_t r[32];
-        tmem_ld32(tO + lane_off + c * 32, r);
-        wait_ld();
-        if (cur_pix >= 0) {
+      for (int i = 0; i < (NCH + 1) / 2; ++i) {
+        if (i < nmine) {
+          wait_ld();
+          // keep one TMEM load in flight while this chunk is normalised and stored
+          if (i + 1 < nmine) tmem_ld32(tO + lane_off + (half + 2 * (i + 1)) * 32, r[(i + 1) & 1]);
+          if (cur_pix >= 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            float o[8];
+            for (int j = 0; j < 32; j += 8) {
+              float o[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[j + e]) * inv_l;
-            stg_stream8(orow + c * 32 + j, o);
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[i & 1][j + e]) * inv_l;
+#if NAF_TC_EXP & 1
+              if (o[0] == 123.456f) stg_stream8(orow + (half + 2 * i) * 32 + j, o);
+#else
+              stg_stream8(orow + (half + 2 * i) * 32 + j, o);
+#endif
+            }
           }
         }
       }
+      wait_ld();
     }
     fence_before_sync();  // O / S columns are rewritten by the next tile's MMAs (after its barriers)
     phase ^= 1;
@@ -388,7 +424,10 @@ bool xattn_cell_tc_supported(const naf_xattn_params& p, const char** why) {
     return false;
   }
   const int tp = taps_pad(p.K);
-  if (tp != 16 && tp != 32 && tp != 64 && tp != 96 && tp != 128) { *why = "kernel_size must be <= 11"; return false; }
+  if (p.K < 3 || (tp != 16 && tp != 32 && tp != 64 && tp != 96 && tp != 128)) {
+    *why = "kernel_size must be 3, 5, 7, 9 or 11";
+    return false;
+  }
   if ((p.Ho / p.h) * (p.Wo / p.w) < 64) { *why = "fewer than 64 pixels per cell"; return false; }
   if (!aligned32(p.q) || !aligned32(p.k) || !aligned32(p.v) || !aligned32(p.out) ||
       (p.q_stride_b % 8) || (p.q_stride_y % 8) || (p.q_stride_x % 8)) {
