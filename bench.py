@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tc"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tc", "cell_tcws"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-d2h", default="sample", choices=["sample", "full"])
     args = ap.parse_args()

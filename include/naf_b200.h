@@ -140,7 +140,8 @@ typedef struct naf_xattn_params {
   int32_t rep_y, rep_x;  /* q is a replicated source map (B,Ho/rep_y,Wo/rep_x,D); see kpool */
 } naf_xattn_params;
 
-enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2, NAF_ALGO_CELL_TC = 3 };
+enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2, NAF_ALGO_CELL_TC = 3,
+       NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline */ };
 
 NAF_API int naf_xattn_fwd_f32(const naf_xattn_params* p, void* stream);
 

@@ -15,8 +15,8 @@ LIB_PATH = os.environ.get("NAF_B200_LIB") or os.path.join(_HERE, "csrc", "libnaf
 ABI_VERSION = 1
 
 NAF_OK, NAF_ERR_BAD_SHAPE, NAF_ERR_UNSUPPORTED, NAF_ERR_WINDOW, NAF_ERR_ALIGNMENT, NAF_ERR_NULL, NAF_ERR_CUDA = range(7)
-ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC = range(4)
-ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TC: "cell_tc"}
+ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS = range(5)
+ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TC: "cell_tc", ALGO_CELL_TCWS: "cell_tcws"}
 
 _fp = C.c_void_p  # device pointers travel as integers
 

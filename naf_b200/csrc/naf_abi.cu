@@ -68,6 +68,10 @@ static int validate_xattn(const naf_xattn_params& p) {
 static int select_algo(const naf_xattn_params& p, bool explain) {
   const char* why = "";
   if (p.algo == NAF_ALGO_GENERIC) return NAF_ALGO_GENERIC;
+  if (p.algo == NAF_ALGO_CELL_TCWS) {
+    if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: pipelined tensor-core cell kernel unsupported: %s", why);
+  }
   if (p.algo == NAF_ALGO_CELL_TC) {
     if (xattn_cell_tc_supported(p, &why)) return NAF_ALGO_CELL_TC;
     return -fail(NAF_ERR_UNSUPPORTED, "xattn: tensor-core cell kernel unsupported: %s", why);
@@ -78,6 +82,7 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
   }
   if (p.algo != NAF_ALGO_AUTO) return -fail(NAF_ERR_UNSUPPORTED, "xattn: unknown algo %d", p.algo);
   (void)explain;
+  if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
   if (xattn_cell_tc_supported(p, &why)) return NAF_ALGO_CELL_TC;
   if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
   return NAF_ALGO_GENERIC;
@@ -158,6 +163,8 @@ int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
   if (algo < 0) return -algo;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (algo) {
+    case NAF_ALGO_CELL_TCWS:
+      return launch_xattn_cell_tcws(p, st);
     case NAF_ALGO_CELL_TC:
       return launch_xattn_cell_tc(p, st);
     case NAF_ALGO_CELL_SIMT:

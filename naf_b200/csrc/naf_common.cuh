@@ -118,6 +118,8 @@ bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_simt(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_tc_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_tc(const naf_xattn_params& p, cudaStream_t st);
+bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why);
+int launch_xattn_cell_tcws(const naf_xattn_params& p, cudaStream_t st);
 int launch_dump_taps(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap, int Ho,
                      int Wo, int h, int w, int K, cudaStream_t st);
 

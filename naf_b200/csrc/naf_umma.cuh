@@ -139,6 +139,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                : "r"(taddr)
                : "memory");
 }
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(r) : "memory");
+}
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]),
                "r"(r[1]), "r"(r[2]), "r"(r[3])

@@ -1,0 +1,560 @@
+// Cell kernel, warp-specialised tensor-core pipeline (tcgen05 / TMEM / bulk-copy epilogue).
+//
+// Same math as naf_xattn_tc.cu (two 3-pass fp16 hi/lo GEMMs per 128-row tile of one low-res cell
+// and head, fp32 accumulation in TMEM), restructured so that HBM loads, tensor-core work, softmax
+// and HBM stores of DIFFERENT tiles overlap inside one persistent CTA per SM:
+//
+//   warps 0-7   "front" : two threads per pixel row.  q half-rows HBM -> registers (prefetched two
+//                          tiles ahead), RoPE, fp16 hi/lo split, tcgen05.st into TMEM (Q is the
+//                          A operand of S = Q Kwin^T straight from TMEM, no smem staging);
+//                          softmax on S (tcgen05.ld), P back to TMEM over S.
+//   warps 8-15  "back"  : drain O from TMEM, normalise, stage the 768-byte row slabs in shared
+//                          memory and hand them to the TMA engine (cp.async.bulk shared->global):
+//                          output stores cost no LSU wavefronts and never stall a warp.  Also
+//                          stages the NEXT item's K / V windows (double buffered).
+//   warp 16     "mma"   : one thread issues every tcgen05.mma in the order
+//                          QK(0) QK(1) PV(0) QK(2) PV(1) ...  and commits to mbarriers.
+//
+// TMEM (512 columns): Q[2] x 64 | S/P[2] x TP | O x DV.   mbarriers carry every hand-off.
+// Tiles are balanced (ceil(npix / ntiles) rows each) so a 28x28 cell is 7 x 112 rows.
+//
+// Reference semantics: src/layers/attentions.py:16-29,53-75; RoPE src/layers/rope.py:137-153.
+#include "naf_common.cuh"
+#include "naf_umma.cuh"
+
+namespace naf {
+
+using namespace umma;
+
+namespace {
+
+constexpr int DQ = 64;
+constexpr int KC = DQ / 8;
+constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 32;
+
+template <int TP>
+struct WsWindowOf { static constexpr int K = TP == 16 ? 3 : TP == 32 ? 5 : TP == 64 ? 7 : TP == 96 ? 9 : 11; };
+
+template <int TP, int DV>
+struct WsCfg {
+  static constexpr int kSmemK = KC * TP * 16;          // one of hi / lo
+  static constexpr int kSmemV = TP * DV * 2;           // one of hi / lo
+  static constexpr int kWin = 2 * kSmemK + 2 * kSmemV; // one window buffer (K hi|lo|V hi|lo)
+  static constexpr int kRowBytes = DV * 4 + 16;        // staged output row + 16 B pad (bank spread)
+  static constexpr int kStage = 128 * kRowBytes;
+  static constexpr int kSmemTotal = 2 * kWin + kStage;
+  static constexpr int kTmemQ = 0;                     // Q[2]: 2 x 64 columns (32 hi + 32 lo)
+  static constexpr int kTmemS = 128;                   // S/P[2]: 2 x TP columns
+  static constexpr int kTmemO = 128 + 2 * TP;          // O: DV columns
+  static constexpr int kTmemL = 128 + 2 * TP + DV;     // row sums l: 4 slots (tile & 3) x 2 halves
+  static constexpr int kTmemUsed = 128 + 2 * TP + DV + 8;
+  static_assert(TP % 16 == 0 && DV % 32 == 0, "bad tile");
+};
+
+__device__ __forceinline__ void ws_split8(const float* x, uint4& hi, uint4& lo) {
+  split2_f16(x[0], x[1], hi.x, lo.x);
+  split2_f16(x[2], x[3], hi.y, lo.y);
+  split2_f16(x[4], x[5], hi.z, lo.z);
+  split2_f16(x[6], x[7], hi.w, lo.w);
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+struct ItemCoord {
+  int b, ci, cj, head;
+};
+__device__ __forceinline__ ItemCoord decode_item(int item, const naf_xattn_params& p) {
+  ItemCoord c;
+  c.head = item % p.heads;
+  item /= p.heads;
+  c.cj = item % p.w;
+  item /= p.w;
+  c.ci = item % p.h;
+  c.b = item / p.h;
+  return c;
+}
+
+// Stage the K and V windows of one item into a window buffer (fp32 -> fp16 hi/lo, UMMA
+// canonical layouts).  Executed by `nthreads` threads with linear id `t`.
+template <int TP, int DV>
+__device__ __forceinline__ void stage_windows(uint8_t* win, const naf_xattn_params& p,
+                                              const ItemCoord& it, int t, int nthreads) {
+  using Cfg = WsCfg<TP, DV>;
+  constexpr int K = WsWindowOf<TP>::K, K2 = K * K;
+  uint8_t* sKhi = win;
+  uint8_t* sKlo = sKhi + Cfg::kSmemK;
+  uint8_t* sVhi = sKlo + Cfg::kSmemK;
+  uint8_t* sVlo = sVhi + Cfg::kSmemV;
+  const int wy0 = window_origin(it.ci, p.h, K);
+  const int wx0 = window_origin(it.cj, p.w, K);
+  // K: canonical K-major [chunk c][tap n][16 B], zero rows for n >= K2
+#pragma unroll 2
+  for (int i = t; i < TP * KC; i += nthreads) {
+    const int n = i % TP, c = i / TP;
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+    if (n < K2) {
+      const int tt = n / K, u = n - tt * K;
+      const float* src = p.k + (int64_t(it.b * p.h + wy0 + tt) * p.w + wx0 + u) * p.D + it.head * DQ + c * 8;
+      float x[8];
+      ldg8(src, x);
+      ws_split8(x, hi, lo);
+    }
+    *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
+    *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
+  }
+  // V: canonical MN-major [tap group][channel group][tap%8][16 B]
+  constexpr int NG = DV / 8;
+#pragma unroll 4
+  for (int i = t; i < TP * NG; i += nthreads) {
+    const int kk = i & 7;
+    const int g = (i >> 3) % NG;
+    const int kg = (i >> 3) / NG;
+    const int k = kg * 8 + kk;
+    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+    if (k < K2) {
+      const int tt = k / K, u = k - tt * K;
+      const float* src = p.v + (int64_t(it.b * p.h + wy0 + tt) * p.w + wx0 + u) * p.C + it.head * DV + g * 8;
+      float x[8];
+      ldg8(src, x);
+      ws_split8(x, hi, lo);
+    }
+    const int off = (kg * NG + g) * 128 + kk * 16;
+    *reinterpret_cast<uint4*>(sVhi + off) = hi;
+    *reinterpret_cast<uint4*>(sVlo + off) = lo;
+  }
+}
+
+}  // namespace
+
+template <int TP, int DV>
+__global__ void __launch_bounds__(NTHREADS, 1)
+xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
+  using Cfg = WsCfg<TP, DV>;
+  constexpr int K2 = WsWindowOf<TP>::K * WsWindowOf<TP>::K;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_win_full[2], bar_o_full, bar_o_free;
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t* win0 = smem;
+  uint8_t* win1 = smem + Cfg::kWin;
+  uint8_t* stage_out = smem + 2 * Cfg::kWin;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int npix = rh * rw;
+  const int ntiles = (npix + 127) >> 7;
+  const int tile_rows = (npix + ntiles - 1) / ntiles;   // balanced tiles, <= 128 rows
+  const int my_items = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+
+  if (warp == 16) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_q_full[s], NFRONT);
+      mbar_init(&bar_s_full[s], 1);
+      mbar_init(&bar_p_full[s], NFRONT);
+      mbar_init(&bar_win_full[s], NBACK);
+    }
+    mbar_init(&bar_o_full, 1);
+    mbar_init(&bar_o_free, NBACK);
+    fence_mbar_init();
+  }
+  // windows of this CTA's first item: staged by everybody
+  if (my_items > 0 && tid < NFRONT + NBACK)
+    stage_windows<TP, DV>(win0, p, decode_item(blockIdx.x, p), tid, NFRONT + NBACK);
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const int total_tiles = my_items * ntiles;
+
+  if (warp < 8) {
+    // ======================================================================== FRONT
+    const int rowgrp = warp & 3, half = warp >> 2;
+    const int row = rowgrp * 32 + lane;
+    const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
+    constexpr int HALF = DQ / 2, P = DQ / 4, SC = TP / 2;
+    const bool rope = p.cos_y != nullptr;
+    const float qscale = p.scale * 1.4426950408889634f;
+
+    float qa[P], qb[P];
+    int q_y = 0, q_x = 0;
+
+    auto issue_q = [&](int g) {   // global tile index of this CTA
+      const int it_seq = g / ntiles, tile = g - it_seq * ntiles;
+      const ItemCoord it = decode_item(blockIdx.x + it_seq * gridDim.x, p);
+      int pi = tile * tile_rows + row;
+      const int lim = min(npix, (tile + 1) * tile_rows);
+      if (row >= tile_rows || pi >= lim) pi = lim - 1;
+      const int py = pi / rw;
+      q_y = it.ci * rh + py;
+      q_x = it.cj * rw + (pi - py * rw);
+      const float* qp = p.q + int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
+                        int64_t(q_y / p.rep_y) * p.q_stride_y + int64_t(q_x / p.rep_x) * p.q_stride_x;
+      ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
+      ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
+      ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
+      ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+    };
+    // rotate + scale + split the prefetched q and write it to TMEM stage s:
+    // columns [0,32) hi, [32,64) lo; two channels per 32-bit column
+    auto stage_q = [&](int s) {
+      if (rope) {
+        const float* ct = half == 0 ? p.cos_y + int64_t(q_y) * P : p.cos_x + int64_t(q_x) * P;
+        const float* st = half == 0 ? p.sin_y + int64_t(q_y) * P : p.sin_x + int64_t(q_x) * P;
+        float c[P], sn[P];
+        ldg8(ct, *reinterpret_cast<float(*)[8]>(&c[0]));
+        ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
+        ldg8(st, *reinterpret_cast<float(*)[8]>(&sn[0]));
+        ldg8(st + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          const float a = qa[j], bb = qb[j];
+          qa[j] = (a * c[j] - bb * sn[j]) * qscale;
+          qb[j] = (bb * c[j] + a * sn[j]) * qscale;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          qa[j] *= qscale;
+          qb[j] *= qscale;
+        }
+      }
+      // channel c lives in packed column c/2: a part -> columns [8h, 8h+8), b part -> [16+8h, ..)
+      const uint32_t tq = tmem + Cfg::kTmemQ + s * 64 + lane_off;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split2_f16(qa[2 * j], qa[2 * j + 1], hi[j], lo[j]);
+      tmem_st8(tq + 8 * half, hi);
+      tmem_st8(tq + 32 + 8 * half, lo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split2_f16(qb[2 * j], qb[2 * j + 1], hi[j], lo[j]);
+      tmem_st8(tq + 16 + 8 * half, hi);
+      tmem_st8(tq + 48 + 8 * half, lo);
+      wait_st();
+      fence_before_sync();
+      mbar_arrive(&bar_q_full[s]);
+    };
+
+    if (total_tiles > 0) {
+      issue_q(0);
+      stage_q(0);
+      if (total_tiles > 1) issue_q(1);
+    }
+    for (int g = 0; g < total_tiles; ++g) {
+      const int s = g & 1;
+      // (a) next tile's Q goes to TMEM early so that QK(g+1) runs under softmax(g)
+      if (g + 1 < total_tiles) {
+        stage_q(s ^ 1);
+        if (g + 2 < total_tiles) issue_q(g + 2);
+      }
+      // (b) softmax of tile g
+      mbar_wait(&bar_s_full[s], (g >> 1) & 1);
+      fence_after_sync();
+      const uint32_t ts = tmem + Cfg::kTmemS + s * TP + lane_off;
+      float m = -INFINITY;
+      uint32_t mine[SC];
+      {
+        // this thread's half of the row stays in registers; the other half is only read for the
+        // row maximum (so the two halves need no cross-warp exchange)
+        const int base = half * SC, other = (1 - half) * SC;
+        if constexpr (SC % 16 == 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 16) tmem_ld16(ts + base + c0, *reinterpret_cast<uint32_t(*)[16]>(&mine[c0]));
+          wait_ld();
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld16(ts + other + c0, r);
+            wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (other + c0 + j < K2) m = fmaxf(m, __uint_as_float(r[j]));
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(ts + base + c0, *reinterpret_cast<uint32_t(*)[8]>(&mine[c0]));
+          wait_ld();
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 8) {
+            uint32_t r[8];
+            tmem_ld8(ts + other + c0, r);
+            wait_ld();
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (other + c0 + j < K2) m = fmaxf(m, __uint_as_float(r[j]));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < SC; ++j)
+          if (base + j < K2) m = fmaxf(m, __uint_as_float(mine[j]));
+      }
+      // the P columns overwrite S columns that the OTHER half may still be reading -> both halves
+      // of a row group must have finished their loads: named barrier over the front group
+      fence_before_sync();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      fence_after_sync();
+      const int tap0 = half * SC;
+      float l = 0.f;
+#pragma unroll
+      for (int j = 0; j < SC; ++j) {
+        const float e = (tap0 + j < K2) ? fast_exp2(__uint_as_float(mine[j]) - m) : 0.f;
+        l += e;
+        mine[j] = __float_as_uint(e);
+      }
+      // row sum for the epilogue: spare TMEM column, slot [tile & 3][half] (the epilogue may lag
+      // two tiles behind, so two slots would not be enough)
+      tmem_st1(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2 + half, __float_as_uint(l));
+      if constexpr (SC % 16 == 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < SC; c0 += 16) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            split2_f16(__uint_as_float(mine[c0 + 2 * j]), __uint_as_float(mine[c0 + 2 * j + 1]), hi[j], lo[j]);
+          tmem_st8(ts + (tap0 + c0) / 2, hi);
+          tmem_st8(ts + TP / 2 + (tap0 + c0) / 2, lo);
+        }
+      } else {
+#pragma unroll
+        for (int c0 = 0; c0 < SC; c0 += 8) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            split2_f16(__uint_as_float(mine[c0 + 2 * j]), __uint_as_float(mine[c0 + 2 * j + 1]), hi[j], lo[j]);
+          tmem_st4(ts + (tap0 + c0) / 2, hi);
+          tmem_st4(ts + TP / 2 + (tap0 + c0) / 2, lo);
+        }
+      }
+      wait_st();
+      fence_before_sync();
+      mbar_arrive(&bar_p_full[s]);   // release: l (smem) and P (TMEM) are visible to the consumers
+    }
+  } else if (warp < 16) {
+    // ======================================================================== BACK
+    const int bw = warp - 8;
+    const int rowgrp = bw & 3, half = bw >> 2;
+    const int row = rowgrp * 32 + lane;
+    const int bt = tid - NFRONT;
+    const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
+    constexpr int HC = DV / 2;            // output columns per thread (contiguous half row)
+    uint8_t* my_stage = stage_out + row * Cfg::kRowBytes + half * HC * 4;
+    int g = 0;
+    for (int it_seq = 0; it_seq < my_items; ++it_seq) {
+      const ItemCoord it = decode_item(blockIdx.x + it_seq * gridDim.x, p);
+      // stage the NEXT item's windows into the other buffer (its last reader, item it_seq-1, has
+      // been fully drained by this group)
+      if (it_seq + 1 < my_items) {
+        uint8_t* nxt = ((it_seq + 1) & 1) ? win1 : win0;
+        stage_windows<TP, DV>(nxt, p, decode_item(blockIdx.x + (it_seq + 1) * gridDim.x, p), bt, NBACK);
+        fence_proxy_async_smem();
+        mbar_arrive(&bar_win_full[(it_seq + 1) & 1]);
+      }
+      float* obase = p.out + int64_t(it.b) * p.Ho * p.Wo * p.C + it.head * DV + half * HC;
+      for (int tile = 0; tile < ntiles; ++tile, ++g) {
+        const int s = g & 1;
+        const int pi = tile * tile_rows + row;
+        const bool valid = row < tile_rows && pi < npix;
+        const int py = pi / rw;
+        const int y = it.ci * rh + py, x = it.cj * rw + (pi - py * rw);
+        // the previous tile's bulk store must have finished READING this thread's staging bytes
+        bulk_wait_read<0>();
+        mbar_wait(&bar_o_full, g & 1);
+        fence_after_sync();
+        uint32_t l0, l1;
+        tmem_ld2(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2, l0, l1);
+        const uint32_t to = tmem + Cfg::kTmemO + lane_off + half * HC;
+        uint32_t r[2][16];
+        tmem_ld16(to, r[0]);
+        wait_ld();
+        const float inv_l = 1.f / (__uint_as_float(l0) + __uint_as_float(l1));
+#pragma unroll
+        for (int c = 0; c < HC / 16; ++c) {
+          wait_ld();
+          if (c + 1 < HC / 16) tmem_ld16(to + (c + 1) * 16, r[(c + 1) & 1]);
+          else {
+            // last chunk is in registers: O may be overwritten by the next PV
+            fence_before_sync();
+            mbar_arrive(&bar_o_free);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            *reinterpret_cast<float4*>(my_stage + (c * 16 + j) * 4) =
+                make_float4(__uint_as_float(r[c & 1][j]) * inv_l, __uint_as_float(r[c & 1][j + 1]) * inv_l,
+                            __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
+          }
+        }
+        // this thread's half row -> TMA engine (it only reads bytes this thread wrote)
+        fence_proxy_async_smem();
+        if (valid) bulk_store(obase + (int64_t(y) * p.Wo + x) * p.C, my_stage, HC * 4);
+        bulk_commit();
+      }
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output writes performed
+  } else {
+    // ======================================================================== MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, TP, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, DV, false, true);
+      const uint32_t tO = tmem + Cfg::kTmemO;
+      auto win_of = [&](int g) { return (((g / ntiles) & 1) ? win1 : win0); };
+      auto issue_qk = [&](int g) {
+        const int s = g & 1;
+        const int it_seq = g / ntiles;
+        if (g - it_seq * ntiles == 0 && it_seq > 0) mbar_wait(&bar_win_full[it_seq & 1], ((it_seq - 1) >> 1) & 1);
+        mbar_wait(&bar_q_full[s], (g >> 1) & 1);
+        fence_after_sync();
+        const uint8_t* w = win_of(g);
+        const uint32_t tq = tmem + Cfg::kTmemQ + s * 64;
+        const uint32_t tS = tmem + Cfg::kTmemS + s * TP;
+        // S = Qhi*Khi^T + Qlo*Khi^T + Qhi*Klo^T
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = tq + (pass == 1 ? 32 : 0);
+          const uint32_t b0 = smem_u32(w + (pass == 2 ? Cfg::kSmemK : 0));
+#pragma unroll
+          for (int kk = 0; kk < DQ / 16; ++kk) {
+            const uint64_t db = make_desc(b0 + kk * 2 * (TP * 16), TP * 16, 128);
+            mma_f16_ts(tS, a0 + kk * 8, db, idesc_qk, (pass | kk) != 0);
+          }
+        }
+        commit(&bar_s_full[s]);
+      };
+      auto issue_pv = [&](int g) {
+        const int s = g & 1;
+        mbar_wait(&bar_p_full[s], (g >> 1) & 1);
+        mbar_wait(&bar_o_free, (g + 1) & 1);   // O drained by the epilogue of tile g-1
+        fence_after_sync();
+        const uint8_t* w = win_of(g);
+        const uint32_t tP = tmem + Cfg::kTmemS + s * TP;
+        // O = Phi*Vhi + Plo*Vhi + Phi*Vlo
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = tP + (pass == 1 ? TP / 2 : 0);
+          const uint32_t b0 = smem_u32(w + 2 * Cfg::kSmemK + (pass == 2 ? Cfg::kSmemV : 0));
+#pragma unroll
+          for (int kk = 0; kk < TP / 16; ++kk) {
+            const uint64_t db = make_desc(b0 + kk * 2 * (DV / 8) * 128, (DV / 8) * 128, 128);
+            mma_f16_ts(tO, a0 + kk * 8, db, idesc_pv, (pass | kk) != 0);
+          }
+        }
+        commit(&bar_o_full);
+      };
+      if (total_tiles > 0) issue_qk(0);
+      for (int g = 0; g < total_tiles; ++g) {
+        if (g + 1 < total_tiles) issue_qk(g + 1);
+        issue_pv(g);
+      }
+    }
+    __syncwarp();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------ host side
+namespace {
+
+int ws_taps_pad(int K) { return (K * K + 15) / 16 * 16; }
+
+template <int TP, int DV>
+int launch_ws(const naf_xattn_params& p, cudaStream_t st) {
+  using Cfg = WsCfg<TP, DV>;
+  auto kern = xattn_cell_tcws_kernel<TP, DV>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemTotal);
+  if (e != cudaSuccess)
+    return fail(NAF_ERR_CUDA, "xattn(cell-tcws): smem opt-in failed: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t items = int64_t(p.B) * p.h * p.w * p.heads;
+  const int grid = int(items < sms ? items : sms);
+  kern<<<grid, NTHREADS, Cfg::kSmemTotal, st>>>(p, p.Ho / p.h, p.Wo / p.w, int(items));
+  return check_launch("xattn_cell_tcws");
+}
+
+template <int TP, int DV>
+constexpr bool ws_fits() {
+  return WsCfg<TP, DV>::kTmemUsed <= 512 && WsCfg<TP, DV>::kSmemTotal + 1024 <= 227 * 1024;
+}
+
+template <int TP, int DV>
+int launch_ws_checked(const naf_xattn_params& p, cudaStream_t st) {
+  if constexpr (ws_fits<TP, DV>()) return launch_ws<TP, DV>(p, st);
+  else return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): tile %dx%d does not fit", TP, DV);
+}
+
+template <int TP>
+int launch_ws_dv(const naf_xattn_params& p, cudaStream_t st) {
+  switch (p.C / p.heads) {
+    case 32: return launch_ws_checked<TP, 32>(p, st);
+    case 64: return launch_ws_checked<TP, 64>(p, st);
+    case 96: return launch_ws_checked<TP, 96>(p, st);
+    case 128: return launch_ws_checked<TP, 128>(p, st);
+    case 192: return launch_ws_checked<TP, 192>(p, st);
+    case 256: return launch_ws_checked<TP, 256>(p, st);
+    default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): value head dim %d", p.C / p.heads);
+  }
+}
+
+template <int TP>
+bool ws_fits_dv(int dv) {
+  switch (dv) {
+    case 32: return ws_fits<TP, 32>();
+    case 64: return ws_fits<TP, 64>();
+    case 96: return ws_fits<TP, 96>();
+    case 128: return ws_fits<TP, 128>();
+    case 192: return ws_fits<TP, 192>();
+    case 256: return ws_fits<TP, 256>();
+    default: return false;
+  }
+}
+
+}  // namespace
+
+bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why) {
+  const int dq = p.D / p.heads, dv = p.C / p.heads;
+  if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
+  if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }
+  if (p.scores) { *why = "score output requested"; return false; }
+  if (dq != DQ) { *why = "head dim must be 64"; return false; }
+  if (p.K < 3) { *why = "kernel_size must be 3, 5, 7, 9 or 11"; return false; }
+  bool fits = false;
+  switch (ws_taps_pad(p.K)) {
+    case 16: fits = ws_fits_dv<16>(dv); break;
+    case 32: fits = ws_fits_dv<32>(dv); break;
+    case 64: fits = ws_fits_dv<64>(dv); break;
+    case 96: fits = ws_fits_dv<96>(dv); break;
+    case 128: fits = ws_fits_dv<128>(dv); break;
+    default: break;
+  }
+  if (!fits) { *why = "window / value tile does not fit shared memory + TMEM of the pipelined kernel"; return false; }
+  if ((p.Ho / p.h) * (p.Wo / p.w) < 64) { *why = "fewer than 64 pixels per cell"; return false; }
+  if (!aligned32(p.q) || !aligned32(p.k) || !aligned32(p.v) || !aligned32(p.out) ||
+      (p.q_stride_b % 8) || (p.q_stride_y % 8) || (p.q_stride_x % 8)) {
+    *why = "pointers/strides not 32-byte aligned";
+    return false;
+  }
+  if (p.cos_y && !(aligned32(p.cos_y) && aligned32(p.sin_y) && aligned32(p.cos_x) && aligned32(p.sin_x))) {
+    *why = "rope tables not 32-byte aligned";
+    return false;
+  }
+  if (int64_t(p.B) * p.h * p.w * p.heads >= (int64_t(1) << 31)) { *why = "too many items"; return false; }
+  return true;
+}
+
+int launch_xattn_cell_tcws(const naf_xattn_params& p, cudaStream_t st) {
+  switch (ws_taps_pad(p.K)) {
+    case 16: return launch_ws_dv<16>(p, st);
+    case 32: return launch_ws_dv<32>(p, st);
+    case 64: return launch_ws_dv<64>(p, st);
+    case 96: return launch_ws_dv<96>(p, st);
+    case 128: return launch_ws_dv<128>(p, st);
+    default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): kernel_size %d", p.K);
+  }
+}
+
+}  // namespace naf
