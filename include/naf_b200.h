@@ -154,6 +154,26 @@ NAF_API int naf_xattn_select_algo(const naf_xattn_params* p);
 NAF_API int naf_xattn_dump_taps_i32(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap,
                             int Ho, int Wo, int h, int w, int K, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Guidance-encoder glue, pixel-major (B,H,W,C) fp32 activations.
+ * Replaces, per EncBlock half (reference src/layers/convolutions.py:55-67): nn.GroupNorm
+ * (statistics + affine), nn.SiLU, the reflect padding of the following Conv2d and the bias add
+ * of the PRECEDING Conv2d (`bias`, may be NULL: the convolutions are then run without bias).
+ *   naf_gn_stats_f32      : sums[b][g] = { sum(y+bias), sum((y+bias)^2) } in double (zeroed here)
+ *   naf_gn_silu_apply_f32 : out = silu(((y+bias) - mean) * rstd * gamma + beta), biased variance,
+ *                           written into a (B, H+2*pad, W+2*pad, C) tensor with reflect padding
+ *                           (pad = 0 or 1, PyTorch "reflect": no edge repeat).
+ * ---------------------------------------------------------------------------------------- */
+/* torch.cat([a, b], dim=channels) of two pixel-major tensors (npix pixels) fused with the bias adds
+ * of the convolutions that produced them (reference src/model/naf.py:33). bias_* may be NULL. */
+NAF_API int naf_concat_bias_nhwc_f32(const float* a, const float* bias_a, int Ca, const float* b,
+                                     const float* bias_b, int Cb, float* out, int64_t npix, void* stream);
+NAF_API int naf_gn_stats_f32(const float* y, const float* bias, double* sums, int B, int64_t HW,
+                             int C, int G, void* stream);
+NAF_API int naf_gn_silu_apply_f32(const float* y, const float* bias, const float* gamma,
+                                  const float* beta, const double* sums, float* out, int B, int H,
+                                  int W, int C, int G, float eps, int pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

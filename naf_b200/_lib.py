@@ -69,6 +69,10 @@ EXPORTS = {
     "naf_rope_kpool_f32": (C.c_int, [C.POINTER(KPoolParams), _fp]),
     "naf_xattn_fwd_f32": (C.c_int, [C.POINTER(XAttnParams), _fp]),
     "naf_xattn_select_algo": (C.c_int, [C.POINTER(XAttnParams)]),
+    "naf_concat_bias_nhwc_f32": (C.c_int, [_fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int64, _fp]),
+    "naf_gn_stats_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_int, _fp]),
+    "naf_gn_silu_apply_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_float, C.c_int, _fp]),
     "naf_xattn_dump_taps_i32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, _fp]),
 }

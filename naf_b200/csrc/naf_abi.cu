@@ -174,6 +174,30 @@ int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
   }
 }
 
+int naf_concat_bias_nhwc_f32(const float* a, const float* bias_a, int Ca, const float* b,
+                             const float* bias_b, int Cb, float* out, int64_t npix, void* stream) {
+  NAF_REQUIRE(a && b && out, NAF_ERR_NULL, "concat_bias: NULL pointer");
+  NAF_REQUIRE(Ca > 0 && Cb > 0 && npix > 0, NAF_ERR_BAD_SHAPE, "concat_bias: bad sizes");
+  return launch_concat_bias(a, bias_a, Ca, b, bias_b, Cb, out, npix, static_cast<cudaStream_t>(stream));
+}
+
+int naf_gn_stats_f32(const float* y, const float* bias, double* sums, int B, int64_t HW, int C, int G,
+                     void* stream) {
+  NAF_REQUIRE(y && sums, NAF_ERR_NULL, "gn_stats: NULL pointer");
+  NAF_REQUIRE(B > 0 && HW > 0 && C > 0 && G > 0 && C % G == 0, NAF_ERR_BAD_SHAPE, "gn_stats: bad sizes");
+  return launch_gn_stats(y, bias, sums, B, HW, C, G, static_cast<cudaStream_t>(stream));
+}
+
+int naf_gn_silu_apply_f32(const float* y, const float* bias, const float* gamma, const float* beta,
+                          const double* sums, float* out, int B, int H, int W, int C, int G, float eps,
+                          int pad, void* stream) {
+  NAF_REQUIRE(y && gamma && beta && sums && out, NAF_ERR_NULL, "gn_silu_apply: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0 && G > 0 && C % G == 0, NAF_ERR_BAD_SHAPE,
+              "gn_silu_apply: bad sizes");
+  return launch_gn_silu_apply(y, bias, gamma, beta, sums, out, B, H, W, C, G, eps, pad,
+                              static_cast<cudaStream_t>(stream));
+}
+
 int naf_xattn_dump_taps_i32(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap,
                             int Ho, int Wo, int h, int w, int K, void* stream) {
   NAF_REQUIRE(idx_out, NAF_ERR_NULL, "dump_taps: NULL output");

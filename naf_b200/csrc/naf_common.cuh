@@ -120,6 +120,13 @@ bool xattn_cell_tc_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_tc(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_tcws(const naf_xattn_params& p, cudaStream_t st);
+int launch_concat_bias(const float* a, const float* bias_a, int Ca, const float* b, const float* bias_b,
+                       int Cb, float* out, int64_t npix, cudaStream_t st);
+int launch_gn_stats(const float* y, const float* bias, double* sums, int B, int64_t HW, int C, int G,
+                    cudaStream_t st);
+int launch_gn_silu_apply(const float* y, const float* bias, const float* gamma, const float* beta,
+                         const double* sums, float* out, int B, int H, int W, int C, int G, float eps,
+                         int pad, cudaStream_t st);
 int launch_dump_taps(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap, int Ho,
                      int Wo, int h, int w, int K, cudaStream_t st);
 

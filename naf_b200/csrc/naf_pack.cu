@@ -47,6 +47,43 @@ int launch_pack_nhwc(const float* src, float* dst, int B, int C, int H, int W, i
   return check_launch("pack_nhwc");
 }
 
+// out[p][0:Ca] = a[p][:] + bias_a ; out[p][Ca:Ca+Cb] = b[p][:] + bias_b   (pixel-major, float4)
+__global__ void __launch_bounds__(256)
+concat_bias_kernel(const float* __restrict__ a, const float* __restrict__ bias_a, int Ca,
+                   const float* __restrict__ b, const float* __restrict__ bias_b, int Cb,
+                   float* __restrict__ out, int64_t npix) {
+  const int qa = Ca >> 2, qb = Cb >> 2, qt = qa + qb;
+  const int64_t total = npix * qt;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int q = int(i % qt);
+    const int64_t p = i / qt;
+    float4 v, bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < qa) {
+      v = ldg_stream(a + p * Ca + 4 * q);
+      if (bias_a) bv = *reinterpret_cast<const float4*>(bias_a + 4 * q);
+    } else {
+      v = ldg_stream(b + p * Cb + 4 * (q - qa));
+      if (bias_b) bv = *reinterpret_cast<const float4*>(bias_b + 4 * (q - qa));
+    }
+    *reinterpret_cast<float4*>(out + p * (Ca + Cb) + 4 * q) =
+        make_float4(v.x + bv.x, v.y + bv.y, v.z + bv.z, v.w + bv.w);
+  }
+}
+
+int launch_concat_bias(const float* a, const float* bias_a, int Ca, const float* b, const float* bias_b,
+                       int Cb, float* out, int64_t npix, cudaStream_t st) {
+  NAF_REQUIRE(Ca % 4 == 0 && Cb % 4 == 0, NAF_ERR_UNSUPPORTED, "concat_bias: channel counts must be multiples of 4");
+  NAF_REQUIRE(aligned16(a) && aligned16(b) && aligned16(out) && (!bias_a || aligned16(bias_a)) &&
+                  (!bias_b || aligned16(bias_b)),
+              NAF_ERR_ALIGNMENT, "concat_bias: 16-byte alignment");
+  const int64_t total = npix * ((Ca + Cb) / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  concat_bias_kernel<<<unsigned(blocks), 256, 0, st>>>(a, bias_a, Ca, b, bias_b, Cb, out, npix);
+  return check_launch("concat_bias");
+}
+
 // One thread per (pixel, tap): writes the linear low-res cell index the kernels gather from.
 __global__ void dump_taps_kernel(int32_t* __restrict__ out, const int32_t* __restrict__ row_tap,
                                  const int32_t* __restrict__ col_tap, int Ho, int Wo, int h, int w,

@@ -1,0 +1,104 @@
+"""Fast forward of the guidance conv encoder (first step).
+
+The reference's `encoder()` (src/layers/convolutions.py:70-95) is a stem conv followed by EncBlocks
+(GroupNorm -> SiLU -> conv -> GroupNorm -> SiLU -> conv, reflect padding, no residual).  Run through
+ATen it costs ~51 ms at 8x3x448x448 of which < 5 ms are the convolutions: the rest is a 64-CTA
+GroupNorm reduction, separate normalise / SiLU / reflection-pad / bias-add passes and cuDNN layout
+conversions.  This module keeps the convolutions on cuDNN (channels_last, no bias) and replaces
+everything between them by two of our kernels per GroupNorm (`naf_gn_stats_f32`,
+`naf_gn_silu_apply_f32`: bias of the previous conv + GroupNorm + SiLU + reflect pad of the next
+conv in one pass) on pixel-major activations.  The result is bit-for-bit the same math (GroupNorm
+moments are accumulated in double), so the golden parity tests of the whole module still apply.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib, ops
+from .layers.convolutions import EncBlock
+
+
+def _conv_ok(conv) -> bool:
+    k = conv.kernel_size
+    return (isinstance(conv, nn.Conv2d) and k[0] == k[1] and k[0] in (1, 3) and conv.stride == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1
+            and (k[0] == 1 or conv.padding_mode == "reflect") and conv.padding == (k[0] // 2, k[0] // 2))
+
+
+def supported(seq) -> bool:
+    """True if `seq` has exactly the structure the fast path implements."""
+    if not isinstance(seq, nn.Sequential) or len(seq) < 1 or not _conv_ok(seq[0]):
+        return False
+    for blk in list(seq)[1:]:
+        if not isinstance(blk, EncBlock) or blk.residual or blk.use_conv_shortcut:
+            return False
+        if not isinstance(blk.activation_fn, nn.SiLU):
+            return False
+        for norm, conv in ((blk.norm1, blk.conv1), (blk.norm2, blk.conv2)):
+            if not isinstance(norm, nn.GroupNorm) or not norm.affine or not _conv_ok(conv):
+                return False
+            Cn, G = norm.num_channels, norm.num_groups
+            if Cn % 4 or (Cn // 4) % G or 256 % (Cn // 4) or (Cn // G) % 4 or G > 64 or conv.in_channels != Cn:
+                return False
+    return True
+
+
+def _weight_cl(conv):
+    """channels_last copy of the conv weight, cached on the module."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version, w.device)
+    cache = getattr(conv, "_naf_wcl", None)
+    if cache is None or cache[0] != key:
+        cache = (key, w.detach().contiguous(memory_format=torch.channels_last))
+        conv._naf_wcl = cache
+    return cache[1]
+
+
+def _conv_nhwc(x_nhwc, conv):
+    """cuDNN convolution on an ALREADY padded pixel-major tensor, no bias; returns pixel-major."""
+    y = F.conv2d(x_nhwc.permute(0, 3, 1, 2), _weight_cl(conv), None)
+    y = y.permute(0, 2, 3, 1)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+def groupnorm_silu(y, prev_bias, norm, pad: int):
+    """silu(GroupNorm(y + prev_bias)) written with a reflect border of `pad`; y is (B,H,W,C)."""
+    B, H, W, Cn = y.shape
+    dev = y.device
+    G = norm.num_groups
+    sums = torch.empty((B, G, 2), device=dev, dtype=torch.float64)
+    out = torch.empty((B, H + 2 * pad, W + 2 * pad, Cn), device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    st = ops._stream(dev)
+    with torch.cuda.device(dev):
+        rc = lib.naf_gn_stats_f32(ops._ptr(y), ops._ptr(prev_bias), ops._ptr(sums), B, H * W, Cn, G, st)
+        _lib.check(rc, "naf_gn_stats_f32")
+        rc = lib.naf_gn_silu_apply_f32(ops._ptr(y), ops._ptr(prev_bias), ops._ptr(norm.weight), ops._ptr(norm.bias),
+                                       ops._ptr(sums), ops._ptr(out), B, H, W, Cn, G, float(norm.eps), pad, st)
+        _lib.check(rc, "naf_gn_silu_apply_f32")
+    ops.LAUNCHES["groupnorm"] = ops.LAUNCHES.get("groupnorm", 0) + 2
+    return out
+
+
+def forward(seq, image):
+    """Pixel-major (B,H,W,C) output of `seq(image)` WITHOUT the bias of the last convolution, and
+    that bias (or None): the caller folds it into the concat pass."""
+    stem = seq[0]
+    k = stem.kernel_size[0]
+    x = image.float()
+    if k == 3:
+        x = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    x = x.contiguous(memory_format=torch.channels_last)
+    y = F.conv2d(x, _weight_cl(stem), None).permute(0, 2, 3, 1)
+    y = y if y.is_contiguous() else y.contiguous()
+    bias = stem.bias
+    for blk in list(seq)[1:]:
+        for norm, conv in ((blk.norm1, blk.conv1), (blk.norm2, blk.conv2)):
+            a = groupnorm_silu(y, bias, norm, conv.kernel_size[0] // 2)
+            y = _conv_nhwc(a, conv)
+            bias = conv.bias
+    return y, bias

@@ -19,7 +19,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import ops
+from .. import encoder_fast, ops
 from ..layers import CrossAttention, RoPE, encoder
 
 
@@ -29,6 +29,7 @@ class ImageEncoder(nn.Module):
         super().__init__()
         self.use_encoder = use_encoder
         self.out_channels = out_channels
+        self.fast_encoder = True   # False: run the conv stacks as plain torch modules
         half = out_channels // 2
         self.encoder = encoder(in_channels, half, kernel_size=1, ks_res=1, num_layers=img_layers)
         self.sem_encoder = encoder(in_channels, half, kernel_size=3, ks_res=3, num_layers=img_layers)
@@ -75,6 +76,12 @@ class ImageEncoder(nn.Module):
         Hs, Ws = image.shape[-2:]
         if not (image.is_cuda and self.use_encoder and Ho % Hs == 0 and Wo % Ws == 0):
             return self.forward_encoder(image, (Ho, Wo)), (1, 1)
+        if (self.fast_encoder and image.dtype == torch.float32 and encoder_fast.supported(self.encoder)
+                and encoder_fast.supported(self.sem_encoder)):
+            # our GroupNorm/SiLU/pad kernels between cuDNN convs, pixel-major end to end
+            ya, ba = encoder_fast.forward(self.encoder, image)
+            yb, bb = encoder_fast.forward(self.sem_encoder, image)
+            return ops.concat_bias_nhwc(ya, ba, yb, bb), (Ho // Hs, Wo // Ws)
         parts = [self.encoder(image), self.sem_encoder(image)]
         return ops.pack_concat_nhwc(parts), (Ho // Hs, Wo // Ws)
 

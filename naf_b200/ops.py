@@ -111,6 +111,22 @@ def pack_concat_nhwc(parts) -> torch.Tensor:
     return out.permute(0, 3, 1, 2)
 
 
+def concat_bias_nhwc(a, bias_a, b, bias_b) -> torch.Tensor:
+    """cat([a + bias_a, b + bias_b], channels) of two pixel-major (B,H,W,C*) tensors in one pass;
+    returns the NCHW-shaped pixel-major view."""
+    dev = _require_cuda(a, b)
+    B, H, W, Ca = a.shape
+    Cb = b.shape[-1]
+    assert a.is_contiguous() and b.is_contiguous() and tuple(b.shape[:3]) == (B, H, W)
+    out = torch.empty((B, H, W, Ca + Cb), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_concat_bias_nhwc_f32(_ptr(a), _ptr(bias_a), Ca, _ptr(b), _ptr(bias_b), Cb,
+                                                  _ptr(out), B * H * W, _stream(dev))
+    _lib.check(rc, "naf_concat_bias_nhwc_f32")
+    LAUNCHES["pack_nhwc"] += 1
+    return out.permute(0, 3, 1, 2)
+
+
 def as_pixel_major(t: torch.Tensor) -> torch.Tensor:
     """NCHW-shaped view whose storage is pixel-major (no copy when it already is)."""
     if t.dtype != torch.float32:
