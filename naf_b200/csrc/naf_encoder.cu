@@ -66,7 +66,6 @@ gn_silu_apply_kernel(const float* __restrict__ y, const float* __restrict__ bias
   const int b = blockIdx.y;
   const int quads = C >> 2;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
-  const int64_t total = int64_t(Hp) * Wp * quads;
   if (threadIdx.x < G) {
     const double cnt = double(H) * W * (C / G);
     const double su = sums[(int64_t(b) * G + threadIdx.x) * 2], sq = sums[(int64_t(b) * G + threadIdx.x) * 2 + 1];
@@ -77,17 +76,22 @@ gn_silu_apply_kernel(const float* __restrict__ y, const float* __restrict__ bias
     s_rstd[threadIdx.x] = float(1.0 / sqrt(var_d + double(eps)));
   }
   __syncthreads();
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += int64_t(gridDim.x) * blockDim.x) {
-    const int q = int(i % quads);
-    const int64_t pp = i / quads;
-    const int xo = int(pp % Wp), yo = int(pp / Wp);
-    int ys = yo - pad, xs = xo - pad;           // reflect (no edge repeat), pad <= 1
-    ys = ys < 0 ? -ys : (ys >= H ? 2 * H - 2 - ys : ys);
+  // one CTA per (padded output row, batch image): 32-bit index math, fully coalesced float4 traffic
+  const int yo = blockIdx.x;
+  int ys = yo - pad;                             // reflect (no edge repeat), pad <= 1
+  ys = ys < 0 ? -ys : (ys >= H ? 2 * H - 2 - ys : ys);
+  const float* yrow = y + (int64_t(b) * H + ys) * int64_t(W) * C;
+  float* orow = out + (int64_t(b) * Hp + yo) * int64_t(Wp) * C;
+  const int n = Wp * quads;
+  const int cpg = C / G;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int xo = i / quads, q = i - xo * quads;
+    int xs = xo - pad;
     xs = xs < 0 ? -xs : (xs >= W ? 2 * W - 2 - xs : xs);
-    const int g = (4 * q) / (C / G);
+    const int g = (4 * q) / cpg;
     const float mean = s_mean[g], rstd = s_rstd[g];
-    const float4 v = *reinterpret_cast<const float4*>(y + ((int64_t(b) * H + ys) * W + xs) * C + 4 * q);
+    const float4 v = ldg_stream(yrow + int64_t(xs) * C + 4 * q);
     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bias) bv = *reinterpret_cast<const float4*>(bias + 4 * q);
     const float4 ga = *reinterpret_cast<const float4*>(gamma + 4 * q);
@@ -99,8 +103,7 @@ gn_silu_apply_kernel(const float* __restrict__ y, const float* __restrict__ bias
       const float t = (r[j] - mean) * rstd * gg[j] + bb[j];
       r[j] = t / (1.f + expf(-t));
     }
-    *reinterpret_cast<float4*>(out + ((int64_t(b) * Hp + yo) * Wp + xo) * C + 4 * q) =
-        make_float4(r[0], r[1], r[2], r[3]);
+    *reinterpret_cast<float4*>(orow + int64_t(xo) * C + 4 * q) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
 
@@ -127,11 +130,8 @@ int launch_gn_silu_apply(const float* y, const float* bias, const float* gamma, 
   NAF_REQUIRE(pad == 0 || (pad == 1 && H >= 2 && W >= 2), NAF_ERR_UNSUPPORTED, "gn_silu_apply: pad must be 0 or 1");
   NAF_REQUIRE(aligned16(y) && aligned16(out) && aligned16(gamma) && aligned16(beta) && (!bias || aligned16(bias)),
               NAF_ERR_ALIGNMENT, "gn_silu_apply: 16-byte alignment");
-  const int64_t total = int64_t(H + 2 * pad) * (W + 2 * pad) * (C / 4);
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (148 * 16 + B - 1) / B;
-  if (blocks > cap) blocks = cap;
-  const dim3 grid = dim3(unsigned(blocks), unsigned(B), 1u);
+  NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "gn_silu_apply: batch too large");
+  const dim3 grid = dim3(unsigned(H + 2 * pad), unsigned(B), 1u);
   gn_silu_apply_kernel<<<grid, 256, 0, st>>>(y, bias, gamma, beta, sums, out, H, W, C, G, eps, pad);
   return check_launch("gn_silu_apply");
 }

@@ -86,6 +86,18 @@ class RoPE(nn.Module):
             self._table_key = key
         return self._tables
 
+    def mean_axis_tables(self, H: int, W: int, ry: int, rx: int):
+        """Tables at (H/ry, W/rx) holding the MEAN cos/sin over each block of ry rows / rx columns
+        (used to pool keys directly from a replicated guidance map; see NAF.upsample_from_guidance)."""
+        cy, sy, cx, sx = self.axis_tables(H, W)
+        key = (self._table_key, ry, rx)
+        if getattr(self, "_mean_key", None) != key:
+            P = cy.shape[1]
+            self._mean_tables = (cy.view(H // ry, ry, P).mean(1).contiguous(), sy.view(H // ry, ry, P).mean(1).contiguous(),
+                                 cx.view(W // rx, rx, P).mean(1).contiguous(), sx.view(W // rx, rx, P).mean(1).contiguous())
+            self._mean_key = key
+        return self._mean_tables
+
     def forward(self, x: Tensor, layout: str = "spatial") -> Tensor:
         B, D, H, W = x.shape
         if D != self.D_head * self.num_heads:

@@ -123,8 +123,18 @@ class NAF(nn.Module):
         D = x.shape[1]
         x = ops.as_pixel_major(x)  # once, shared by both kernels
         fused = rope.D_head == D // self.upsampler.num_heads
-        k, q = ops.rope_kpool(x, tables, rope.num_heads, pooled_hw=features.shape[-2:],
-                              want_q=not fused, rep=rep)
+        h, w = features.shape[-2:]
+        ry, rx = int(rep[0]), int(rep[1])
+        if fused and (ry > 1 or rx > 1) and Ho % h == 0 and Wo % w == 0 and (Ho // h) % ry == 0 \
+                and (Wo // w) % rx == 0:
+            # Key pooling over replicated guidance: every source pixel stands for an ry x rx block
+            # whose rotations differ only through the angles, and the rotation is linear, so the
+            # block mean of RoPE(x) is x rotated by the block-MEAN cos/sin.  Pool the source map
+            # with mean tables: 1/(ry*rx) of the work, identical result up to summation order.
+            k, q = ops.rope_kpool(x, rope.mean_axis_tables(Ho, Wo, ry, rx), rope.num_heads,
+                                  pooled_hw=(h, w), want_q=False)
+        else:
+            k, q = ops.rope_kpool(x, tables, rope.num_heads, pooled_hw=(h, w), want_q=not fused, rep=rep)
         if fused:
             return self.upsampler(x, k, features, return_weights=return_weights, rope_tables=tables,
                                   rep=rep)
