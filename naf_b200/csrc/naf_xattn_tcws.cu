@@ -8,14 +8,16 @@
 //                          tiles ahead), RoPE, fp16 hi/lo split, tcgen05.st into TMEM (Q is the
 //                          A operand of S = Q Kwin^T straight from TMEM, no smem staging);
 //                          softmax on S (tcgen05.ld), P back to TMEM over S.
-//   warps 8-15  "back"  : drain O from TMEM, normalise, stage the 768-byte row slabs in shared
+//   warps 8-15  "back"  : drain O from TMEM, normalise, stage the output row slabs in shared
 //                          memory and hand them to the TMA engine (cp.async.bulk shared->global):
 //                          output stores cost no LSU wavefronts and never stall a warp.  Also
 //                          stages the NEXT item's K / V windows (double buffered).
 //   warp 16     "mma"   : one thread issues every tcgen05.mma in the order
 //                          QK(0) QK(1) PV(0) QK(2) PV(1) ...  and commits to mbarriers.
 //
-// TMEM (512 columns): Q[2] x 64 | S/P[2] x TP | O x DV.   mbarriers carry every hand-off.
+// An "item" is (batch, cell, head, value-slab): wide value heads (dv = 256 with an 11x11 window)
+// are split into `vsplit` slabs of DV channels so that windows and accumulators fit; the slabs of
+// one head recompute the (cheap) scores.  TMEM: Q x 64 | S/P[2] x TP | O x DV | l x 8 columns.
 // Tiles are balanced (ceil(npix / ntiles) rows each) so a 28x28 cell is 7 x 112 rows.
 //
 // Reference semantics: src/layers/attentions.py:16-29,53-75; RoPE src/layers/rope.py:137-153.
@@ -31,24 +33,34 @@ namespace {
 constexpr int DQ = 64;
 constexpr int KC = DQ / 8;
 constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 32;
+constexpr int MMA_WARP = (NFRONT + NBACK) / 32;
+#ifndef NAF_WS_MEXCH
+#define NAF_WS_MEXCH 1   // row-max exchange between the two row halves: 1 = smem pad, 0 = re-read S from TMEM
+#endif
 
 template <int TP>
 struct WsWindowOf { static constexpr int K = TP == 16 ? 3 : TP == 32 ? 5 : TP == 64 ? 7 : TP == 96 ? 9 : 11; };
 
-template <int TP, int DV>
+// TP: padded taps; DV: value channels per item; ROUNDS: staging rounds of the epilogue
+template <int TP, int DV, int ROUNDS>
 struct WsCfg {
   static constexpr int kSmemK = KC * TP * 16;          // one of hi / lo
   static constexpr int kSmemV = TP * DV * 2;           // one of hi / lo
   static constexpr int kWin = 2 * kSmemK + 2 * kSmemV; // one window buffer (K hi|lo|V hi|lo)
-  static constexpr int kRowBytes = DV * 4 + 16;        // staged output row + 16 B pad (bank spread)
+  static constexpr int kRoundCols = DV / ROUNDS;       // output columns staged per round
+  static constexpr int kRowBytes = kRoundCols * 4 + 16;  // staged row + 16 B pad (bank spread)
   static constexpr int kStage = 128 * kRowBytes;
   static constexpr int kSmemTotal = 2 * kWin + kStage;
-  static constexpr int kTmemQ = 0;                     // Q[2]: 2 x 64 columns (32 hi + 32 lo)
-  static constexpr int kTmemS = 128;                   // S/P[2]: 2 x TP columns
-  static constexpr int kTmemO = 128 + 2 * TP;          // O: DV columns
-  static constexpr int kTmemL = 128 + 2 * TP + DV;     // row sums l: 4 slots (tile & 3) x 2 halves
-  static constexpr int kTmemUsed = 128 + 2 * TP + DV + 8;
-  static_assert(TP % 16 == 0 && DV % 32 == 0, "bad tile");
+  // Q: 64 columns per stage (32 hi + 32 lo); double buffered when TMEM allows, so that the next
+  // tile's Q is staged while the tensor core still works on QK of the current one
+  static constexpr int kQStages = (128 + 2 * TP + DV + 8 <= 512) ? 2 : 1;
+  static constexpr int kTmemQ = 0;
+  static constexpr int kTmemS = 64 * kQStages;         // S/P[2]: 2 x TP columns
+  static constexpr int kTmemO = kTmemS + 2 * TP;       // O: DV columns
+  static constexpr int kTmemL = kTmemO + DV;           // row sums l: 4 slots (tile & 3) x 2 halves
+  static constexpr int kTmemUsed = kTmemL + 8;
+  static constexpr bool kFits = kTmemUsed <= 512 && kSmemTotal + 1024 <= 227 * 1024 &&
+                                (DV % ROUNDS) == 0 && (kRoundCols % 32) == 0;
 };
 
 __device__ __forceinline__ void ws_split8(const float* x, uint4& hi, uint4& lo) {
@@ -62,26 +74,45 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
 
-struct ItemCoord {
-  int b, ci, cj, head;
+// Division by a launch-constant divisor as multiply-high + shift (exact for the small operands
+// used here: n < 2^31 / d, d <= 2^15); the table lives in the kernel parameter constant bank, so
+// the per-tile index arithmetic of 272 threads costs no registers and ~3 instructions per divide.
+struct FastDiv {
+  uint32_t d, magic, shift;
 };
-__device__ __forceinline__ ItemCoord decode_item(int item, const naf_xattn_params& p) {
+struct WsDivs {
+  FastDiv ntiles, vsplit, heads, w, h, rw, rep_y, rep_x;
+};
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return f.magic == 0 ? (n >> f.shift) : int(__umulhi(uint32_t(n), f.magic) >> f.shift);
+}
+
+struct ItemCoord {
+  int b, ci, cj, head, vh;
+};
+__device__ __forceinline__ ItemCoord decode_item(int item, const WsDivs& dv) {
   ItemCoord c;
-  c.head = item % p.heads;
-  item /= p.heads;
-  c.cj = item % p.w;
-  item /= p.w;
-  c.ci = item % p.h;
-  c.b = item / p.h;
+  int q = fdiv(item, dv.vsplit);
+  c.vh = item - q * int(dv.vsplit.d);
+  item = q;
+  q = fdiv(item, dv.heads);
+  c.head = item - q * int(dv.heads.d);
+  item = q;
+  q = fdiv(item, dv.w);
+  c.cj = item - q * int(dv.w.d);
+  item = q;
+  q = fdiv(item, dv.h);
+  c.ci = item - q * int(dv.h.d);
+  c.b = q;
   return c;
 }
 
 // Stage the K and V windows of one item into a window buffer (fp32 -> fp16 hi/lo, UMMA
 // canonical layouts).  Executed by `nthreads` threads with linear id `t`.
-template <int TP, int DV>
+template <int TP, int DV, int ROUNDS>
 __device__ __forceinline__ void stage_windows(uint8_t* win, const naf_xattn_params& p,
-                                              const ItemCoord& it, int t, int nthreads) {
-  using Cfg = WsCfg<TP, DV>;
+                                              const ItemCoord& it, int vchan0, int t, int nthreads) {
+  using Cfg = WsCfg<TP, DV, ROUNDS>;
   constexpr int K = WsWindowOf<TP>::K, K2 = K * K;
   uint8_t* sKhi = win;
   uint8_t* sKlo = sKhi + Cfg::kSmemK;
@@ -115,7 +146,7 @@ __device__ __forceinline__ void stage_windows(uint8_t* win, const naf_xattn_para
     uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
     if (k < K2) {
       const int tt = k / K, u = k - tt * K;
-      const float* src = p.v + (int64_t(it.b * p.h + wy0 + tt) * p.w + wx0 + u) * p.C + it.head * DV + g * 8;
+      const float* src = p.v + (int64_t(it.b * p.h + wy0 + tt) * p.w + wx0 + u) * p.C + vchan0 + g * 8;
       float x[8];
       ldg8(src, x);
       ws_split8(x, hi, lo);
@@ -128,10 +159,10 @@ __device__ __forceinline__ void stage_windows(uint8_t* win, const naf_xattn_para
 
 }  // namespace
 
-template <int TP, int DV>
+template <int TP, int DV, int ROUNDS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
-  using Cfg = WsCfg<TP, DV>;
+xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vsplit, WsDivs dv) {
+  using Cfg = WsCfg<TP, DV, ROUNDS>;
   constexpr int K2 = WsWindowOf<TP>::K * WsWindowOf<TP>::K;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_win_full[2], bar_o_full, bar_o_free;
@@ -146,8 +177,11 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
   const int ntiles = (npix + 127) >> 7;
   const int tile_rows = (npix + ntiles - 1) / ntiles;   // balanced tiles, <= 128 rows
   const int my_items = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  const int dv_full = p.C / p.heads;                    // = vsplit * DV
+  auto item_of = [&](int it_seq) { return decode_item(blockIdx.x + it_seq * gridDim.x, dv); };
+  auto vchan_of = [&](const ItemCoord& it) { return it.head * dv_full + it.vh * DV; };
 
-  if (warp == 16) tmem_alloc(&tmem_base_s, 512);
+  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_q_full[s], NFRONT);
@@ -160,8 +194,10 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
     fence_mbar_init();
   }
   // windows of this CTA's first item: staged by everybody
-  if (my_items > 0 && tid < NFRONT + NBACK)
-    stage_windows<TP, DV>(win0, p, decode_item(blockIdx.x, p), tid, NFRONT + NBACK);
+  if (my_items > 0 && tid < NFRONT + NBACK) {
+    const ItemCoord it0 = item_of(0);
+    stage_windows<TP, DV, ROUNDS>(win0, p, it0, vchan_of(it0), tid, NFRONT + NBACK);
+  }
   fence_proxy_async_smem();
   fence_before_sync();
   __syncthreads();
@@ -181,25 +217,28 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
     float qa[P], qb[P];
     int q_y = 0, q_x = 0;
 
-    auto issue_q = [&](int g) {   // global tile index of this CTA
-      const int it_seq = g / ntiles, tile = g - it_seq * ntiles;
-      const ItemCoord it = decode_item(blockIdx.x + it_seq * gridDim.x, p);
+    int f_g = 0;   // issue_q is called for g = 0, 1, 2, ... in order
+    auto issue_q = [&]() {
+      const int g = f_g++;
+      const int it_seq = fdiv(g, dv.ntiles), tile = g - it_seq * ntiles;
+      const ItemCoord it = item_of(it_seq);
       int pi = tile * tile_rows + row;
       const int lim = min(npix, (tile + 1) * tile_rows);
       if (row >= tile_rows || pi >= lim) pi = lim - 1;
-      const int py = pi / rw;
+      const int py = fdiv(pi, dv.rw);
       q_y = it.ci * rh + py;
       q_x = it.cj * rw + (pi - py * rw);
       const float* qp = p.q + int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
-                        int64_t(q_y / p.rep_y) * p.q_stride_y + int64_t(q_x / p.rep_x) * p.q_stride_x;
+                        int64_t(fdiv(q_y, dv.rep_y)) * p.q_stride_y + int64_t(fdiv(q_x, dv.rep_x)) * p.q_stride_x;
       ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
       ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
       ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
       ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
     };
-    // rotate + scale + split the prefetched q and write it to TMEM stage s:
+    // rotate + scale + split the prefetched q and write it to TMEM:
     // columns [0,32) hi, [32,64) lo; two channels per 32-bit column
-    auto stage_q = [&](int s) {
+    constexpr int QS = Cfg::kQStages;
+    auto stage_q = [&](int g) {   // g: the tile whose q is in the registers
       if (rope) {
         const float* ct = half == 0 ? p.cos_y + int64_t(q_y) * P : p.cos_x + int64_t(q_x) * P;
         const float* st = half == 0 ? p.sin_y + int64_t(q_y) * P : p.sin_x + int64_t(q_x) * P;
@@ -222,7 +261,7 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
         }
       }
       // channel c lives in packed column c/2: a part -> columns [8h, 8h+8), b part -> [16+8h, ..)
-      const uint32_t tq = tmem + Cfg::kTmemQ + s * 64 + lane_off;
+      const uint32_t tq = tmem + Cfg::kTmemQ + (QS == 2 ? (g & 1) * 64 : 0) + lane_off;
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) split2_f16(qa[2 * j], qa[2 * j + 1], hi[j], lo[j]);
@@ -234,67 +273,79 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
       tmem_st8(tq + 48 + 8 * half, lo);
       wait_st();
       fence_before_sync();
-      mbar_arrive(&bar_q_full[s]);
+      mbar_arrive(&bar_q_full[QS == 2 ? (g & 1) : 0]);
     };
 
     if (total_tiles > 0) {
-      issue_q(0);
+      issue_q();
       stage_q(0);
-      if (total_tiles > 1) issue_q(1);
+      if (total_tiles > 1) issue_q();
     }
     for (int g = 0; g < total_tiles; ++g) {
       const int s = g & 1;
-      // (a) next tile's Q goes to TMEM early so that QK(g+1) runs under softmax(g)
-      if (g + 1 < total_tiles) {
-        stage_q(s ^ 1);
-        if (g + 2 < total_tiles) issue_q(g + 2);
+      // (a) next tile's Q goes to TMEM early so that QK(g+1) runs under softmax(g).  With two Q
+      // stages the buffer of tile g+1 was released by QK(g-1) (observed through s_full(g-1) in the
+      // previous iteration); with one stage QK(g) itself must have finished first.
+      if constexpr (QS == 2) {
+        if (g + 1 < total_tiles) {
+          stage_q(g + 1);
+          if (g + 2 < total_tiles) issue_q();
+        }
       }
-      // (b) softmax of tile g
       mbar_wait(&bar_s_full[s], (g >> 1) & 1);
       fence_after_sync();
+      if constexpr (QS == 1) {
+        if (g + 1 < total_tiles) {
+          stage_q(g + 1);
+          if (g + 2 < total_tiles) issue_q();
+        }
+      }
+      // (b) softmax of tile g
       const uint32_t ts = tmem + Cfg::kTmemS + s * TP + lane_off;
       float m = -INFINITY;
       uint32_t mine[SC];
       {
-        // this thread's half of the row stays in registers; the other half is only read for the
-        // row maximum (so the two halves need no cross-warp exchange)
-        const int base = half * SC, other = (1 - half) * SC;
+        const int base = half * SC;
         if constexpr (SC % 16 == 0) {
 #pragma unroll
           for (int c0 = 0; c0 < SC; c0 += 16) tmem_ld16(ts + base + c0, *reinterpret_cast<uint32_t(*)[16]>(&mine[c0]));
-          wait_ld();
-#pragma unroll
-          for (int c0 = 0; c0 < SC; c0 += 16) {
-            uint32_t r[16];
-            tmem_ld16(ts + other + c0, r);
-            wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (other + c0 + j < K2) m = fmaxf(m, __uint_as_float(r[j]));
-          }
         } else {
 #pragma unroll
           for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(ts + base + c0, *reinterpret_cast<uint32_t(*)[8]>(&mine[c0]));
-          wait_ld();
-#pragma unroll
-          for (int c0 = 0; c0 < SC; c0 += 8) {
-            uint32_t r[8];
-            tmem_ld8(ts + other + c0, r);
-            wait_ld();
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (other + c0 + j < K2) m = fmaxf(m, __uint_as_float(r[j]));
-          }
         }
+        wait_ld();
 #pragma unroll
         for (int j = 0; j < SC; ++j)
           if (base + j < K2) m = fmaxf(m, __uint_as_float(mine[j]));
       }
-      // the P columns overwrite S columns that the OTHER half may still be reading -> both halves
-      // of a row group must have finished their loads: named barrier over the front group
+#if NAF_WS_MEXCH
+      // The two halves of a row exchange their partial maxima through the 16-byte pad of the
+      // row's staging slot (slot [tile parity][half]), and the same named barrier orders the S
+      // reads of both halves before P overwrites the S columns.
+      float* mpad = reinterpret_cast<float*>(stage_out + row * Cfg::kRowBytes + Cfg::kRoundCols * 4) + s * 2;
+      mpad[half] = m;
       fence_before_sync();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       fence_after_sync();
+      m = fmaxf(m, mpad[half ^ 1]);
+#else
+      {
+        // the other half of the row is only read for the row maximum
+        const int other = (1 - half) * SC;
+#pragma unroll
+        for (int c0 = 0; c0 < SC; c0 += 8) {
+          uint32_t r[8];
+          tmem_ld8(ts + other + c0, r);
+          wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (other + c0 + j < K2) m = fmaxf(m, __uint_as_float(r[j]));
+        }
+      }
+      fence_before_sync();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      fence_after_sync();
+#endif
       const int tap0 = half * SC;
       float l = 0.f;
 #pragma unroll
@@ -329,66 +380,74 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
       }
       wait_st();
       fence_before_sync();
-      mbar_arrive(&bar_p_full[s]);   // release: l (smem) and P (TMEM) are visible to the consumers
+      mbar_arrive(&bar_p_full[s]);   // release: l and P (TMEM) are visible to the consumers
     }
-  } else if (warp < 16) {
-    // ======================================================================== BACK
+  } else if (warp < MMA_WARP) {
+    // ======================================================================== BACK (two threads per row)
     const int bw = warp - 8;
     const int rowgrp = bw & 3, half = bw >> 2;
     const int row = rowgrp * 32 + lane;
     const int bt = tid - NFRONT;
     const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
-    constexpr int HC = DV / 2;            // output columns per thread (contiguous half row)
+    constexpr int RC = Cfg::kRoundCols;   // output columns staged per round
+    constexpr int HC = RC / 2;            // ... of which this thread owns a contiguous half
     uint8_t* my_stage = stage_out + row * Cfg::kRowBytes + half * HC * 4;
     int g = 0;
     for (int it_seq = 0; it_seq < my_items; ++it_seq) {
-      const ItemCoord it = decode_item(blockIdx.x + it_seq * gridDim.x, p);
+      const ItemCoord it = item_of(it_seq);
       // stage the NEXT item's windows into the other buffer (its last reader, item it_seq-1, has
       // been fully drained by this group)
       if (it_seq + 1 < my_items) {
         uint8_t* nxt = ((it_seq + 1) & 1) ? win1 : win0;
-        stage_windows<TP, DV>(nxt, p, decode_item(blockIdx.x + (it_seq + 1) * gridDim.x, p), bt, NBACK);
+        const ItemCoord itn = item_of(it_seq + 1);
+        stage_windows<TP, DV, ROUNDS>(nxt, p, itn, vchan_of(itn), bt, NBACK);
         fence_proxy_async_smem();
         mbar_arrive(&bar_win_full[(it_seq + 1) & 1]);
       }
-      float* obase = p.out + int64_t(it.b) * p.Ho * p.Wo * p.C + it.head * DV + half * HC;
+      float* obase = p.out + int64_t(it.b) * p.Ho * p.Wo * p.C + vchan_of(it) + half * HC;
       for (int tile = 0; tile < ntiles; ++tile, ++g) {
-        const int s = g & 1;
         const int pi = tile * tile_rows + row;
         const bool valid = row < tile_rows && pi < npix;
-        const int py = pi / rw;
+        const int py = fdiv(pi, dv.rw);
         const int y = it.ci * rh + py, x = it.cj * rw + (pi - py * rw);
-        // the previous tile's bulk store must have finished READING this thread's staging bytes
-        bulk_wait_read<0>();
-        mbar_wait(&bar_o_full, g & 1);
-        fence_after_sync();
-        uint32_t l0, l1;
-        tmem_ld2(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2, l0, l1);
-        const uint32_t to = tmem + Cfg::kTmemO + lane_off + half * HC;
-        uint32_t r[2][16];
-        tmem_ld16(to, r[0]);
-        wait_ld();
-        const float inv_l = 1.f / (__uint_as_float(l0) + __uint_as_float(l1));
+        float* orow = obase + (int64_t(y) * p.Wo + x) * p.C;
+        float inv_l = 0.f;
 #pragma unroll
-        for (int c = 0; c < HC / 16; ++c) {
-          wait_ld();
-          if (c + 1 < HC / 16) tmem_ld16(to + (c + 1) * 16, r[(c + 1) & 1]);
-          else {
-            // last chunk is in registers: O may be overwritten by the next PV
-            fence_before_sync();
-            mbar_arrive(&bar_o_free);
+        for (int rd = 0; rd < ROUNDS; ++rd) {
+          // the previous bulk store must have finished READING this thread's staging bytes
+          bulk_wait_read<0>();
+          if (rd == 0) {
+            mbar_wait(&bar_o_full, g & 1);
+            fence_after_sync();
+            uint32_t l0, l1;
+            tmem_ld2(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2, l0, l1);
+            wait_ld();
+            inv_l = 1.f / (__uint_as_float(l0) + __uint_as_float(l1));
           }
+          const uint32_t to = tmem + Cfg::kTmemO + lane_off + rd * RC + half * HC;
+          uint32_t r[2][16];
+          tmem_ld16(to, r[0]);
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            *reinterpret_cast<float4*>(my_stage + (c * 16 + j) * 4) =
-                make_float4(__uint_as_float(r[c & 1][j]) * inv_l, __uint_as_float(r[c & 1][j + 1]) * inv_l,
-                            __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
+          for (int c = 0; c < HC / 16; ++c) {
+            wait_ld();
+            if (c + 1 < HC / 16) tmem_ld16(to + (c + 1) * 16, r[(c + 1) & 1]);
+            else if (rd == ROUNDS - 1) {
+              // the whole O row is in registers / staged: the next PV may overwrite O
+              fence_before_sync();
+              mbar_arrive(&bar_o_free);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              *reinterpret_cast<float4*>(my_stage + (c * 16 + j) * 4) =
+                  make_float4(__uint_as_float(r[c & 1][j]) * inv_l, __uint_as_float(r[c & 1][j + 1]) * inv_l,
+                              __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
+            }
           }
+          // this thread's slab -> TMA engine (it only reads bytes this thread wrote)
+          fence_proxy_async_smem();
+          if (valid) bulk_store(orow + rd * RC, my_stage, HC * 4);
+          bulk_commit();
         }
-        // this thread's half row -> TMA engine (it only reads bytes this thread wrote)
-        fence_proxy_async_smem();
-        if (valid) bulk_store(obase + (int64_t(y) * p.Wo + x) * p.C, my_stage, HC * 4);
-        bulk_commit();
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output writes performed
@@ -398,15 +457,18 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, TP, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, DV, false, true);
       const uint32_t tO = tmem + Cfg::kTmemO;
-      auto win_of = [&](int g) { return (((g / ntiles) & 1) ? win1 : win0); };
+      constexpr int QS = Cfg::kQStages;
+      int qk_seq = 0, qk_tile = 0, pv_seq = 0, pv_tile = 0;   // (item, tile) of the next QK / PV
       auto issue_qk = [&](int g) {
         const int s = g & 1;
-        const int it_seq = g / ntiles;
-        if (g - it_seq * ntiles == 0 && it_seq > 0) mbar_wait(&bar_win_full[it_seq & 1], ((it_seq - 1) >> 1) & 1);
-        mbar_wait(&bar_q_full[s], (g >> 1) & 1);
+        const int it_seq = qk_seq;
+        if (qk_tile == 0 && it_seq > 0) mbar_wait(&bar_win_full[it_seq & 1], ((it_seq - 1) >> 1) & 1);
+        const uint8_t* w = (it_seq & 1) ? win1 : win0;
+        if (++qk_tile == ntiles) { qk_tile = 0; ++qk_seq; }
+        if constexpr (QS == 2) mbar_wait(&bar_q_full[s], (g >> 1) & 1);
+        else mbar_wait(&bar_q_full[0], g & 1);
         fence_after_sync();
-        const uint8_t* w = win_of(g);
-        const uint32_t tq = tmem + Cfg::kTmemQ + s * 64;
+        const uint32_t tq = tmem + Cfg::kTmemQ + (QS == 2 ? s * 64 : 0);
         const uint32_t tS = tmem + Cfg::kTmemS + s * TP;
         // S = Qhi*Khi^T + Qlo*Khi^T + Qhi*Klo^T
 #pragma unroll
@@ -426,7 +488,8 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
         mbar_wait(&bar_p_full[s], (g >> 1) & 1);
         mbar_wait(&bar_o_free, (g + 1) & 1);   // O drained by the epilogue of tile g-1
         fence_after_sync();
-        const uint8_t* w = win_of(g);
+        const uint8_t* w = (pv_seq & 1) ? win1 : win0;
+        if (++pv_tile == ntiles) { pv_tile = 0; ++pv_seq; }
         const uint32_t tP = tmem + Cfg::kTmemS + s * TP;
         // O = Phi*Vhi + Plo*Vhi + Phi*Vlo
 #pragma unroll
@@ -452,7 +515,7 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items) {
 
   fence_before_sync();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------ host side
@@ -460,56 +523,129 @@ namespace {
 
 int ws_taps_pad(int K) { return (K * K + 15) / 16 * 16; }
 
-template <int TP, int DV>
-int launch_ws(const naf_xattn_params& p, cudaStream_t st) {
-  using Cfg = WsCfg<TP, DV>;
-  auto kern = xattn_cell_tcws_kernel<TP, DV>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemTotal);
-  if (e != cudaSuccess)
-    return fail(NAF_ERR_CUDA, "xattn(cell-tcws): smem opt-in failed: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t items = int64_t(p.B) * p.h * p.w * p.heads;
-  const int grid = int(items < sms ? items : sms);
-  kern<<<grid, NTHREADS, Cfg::kSmemTotal, st>>>(p, p.Ho / p.h, p.Wo / p.w, int(items));
-  return check_launch("xattn_cell_tcws");
+FastDiv make_fastdiv(uint32_t d) {
+  // power of two: plain shift (magic == 0).  Otherwise, with s = ceil(log2 d):
+  // magic = ceil(2^(31+s) / d) in (2^31, 2^32), n / d == umulhi(n, magic) >> (s - 1), exact for
+  // every 0 <= n < 2^31.
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  if ((d & (d - 1)) == 0) {
+    f.magic = 0;
+    f.shift = s;
+  } else {
+    f.magic = uint32_t(((uint64_t(1) << (31 + s)) + d - 1) / d);
+    f.shift = s - 1;
+  }
+  return f;
 }
 
-template <int TP, int DV>
-constexpr bool ws_fits() {
-  return WsCfg<TP, DV>::kTmemUsed <= 512 && WsCfg<TP, DV>::kSmemTotal + 1024 <= 227 * 1024;
-}
-
-template <int TP, int DV>
-int launch_ws_checked(const naf_xattn_params& p, cudaStream_t st) {
-  if constexpr (ws_fits<TP, DV>()) return launch_ws<TP, DV>(p, st);
-  else return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): tile %dx%d does not fit", TP, DV);
-}
-
-template <int TP>
-int launch_ws_dv(const naf_xattn_params& p, cudaStream_t st) {
-  switch (p.C / p.heads) {
-    case 32: return launch_ws_checked<TP, 32>(p, st);
-    case 64: return launch_ws_checked<TP, 64>(p, st);
-    case 96: return launch_ws_checked<TP, 96>(p, st);
-    case 128: return launch_ws_checked<TP, 128>(p, st);
-    case 192: return launch_ws_checked<TP, 192>(p, st);
-    case 256: return launch_ws_checked<TP, 256>(p, st);
-    default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): value head dim %d", p.C / p.heads);
+template <int TP, int DV, int ROUNDS>
+int launch_ws(const naf_xattn_params& p, int vsplit, cudaStream_t st) {
+  using Cfg = WsCfg<TP, DV, ROUNDS>;
+  if constexpr (!Cfg::kFits) {
+    return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): tile %dx%d/%d does not fit", TP, DV, ROUNDS);
+  } else {
+    auto kern = xattn_cell_tcws_kernel<TP, DV, ROUNDS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemTotal);
+    if (e != cudaSuccess)
+      return fail(NAF_ERR_CUDA, "xattn(cell-tcws): smem opt-in failed: %s", cudaGetErrorString(e));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t items = int64_t(p.B) * p.h * p.w * p.heads * vsplit;
+    const int grid = int(items < sms ? items : sms);
+    const int rh = p.Ho / p.h, rw = p.Wo / p.w;
+    WsDivs dv;
+    dv.ntiles = make_fastdiv(uint32_t((rh * rw + 127) / 128));
+    dv.vsplit = make_fastdiv(uint32_t(vsplit));
+    dv.heads = make_fastdiv(uint32_t(p.heads));
+    dv.w = make_fastdiv(uint32_t(p.w));
+    dv.h = make_fastdiv(uint32_t(p.h));
+    dv.rw = make_fastdiv(uint32_t(rw));
+    dv.rep_y = make_fastdiv(uint32_t(p.rep_y));
+    dv.rep_x = make_fastdiv(uint32_t(p.rep_x));
+    kern<<<grid, NTHREADS, Cfg::kSmemTotal, st>>>(p, rh, rw, int(items), vsplit, dv);
+    return check_launch("xattn_cell_tcws");
   }
 }
 
+// The plan for a (taps, value head dim) pair: slab width DV = dv / vsplit and staging rounds,
+// the first combination (fewest slabs, then fewest rounds) that fits TMEM and shared memory.
+struct WsPlan {
+  int dv_tile = 0, rounds = 0;
+};
+
+template <int TP, int DV>
+constexpr int ws_rounds() {
+  if (WsCfg<TP, DV, 1>::kFits) return 1;
+  if (DV % 64 == 0 && WsCfg<TP, DV, 2>::kFits) return 2;
+  if (DV % 128 == 0 && WsCfg<TP, DV, 4>::kFits) return 4;
+  return 0;
+}
+
 template <int TP>
-bool ws_fits_dv(int dv) {
-  switch (dv) {
-    case 32: return ws_fits<TP, 32>();
-    case 64: return ws_fits<TP, 64>();
-    case 96: return ws_fits<TP, 96>();
-    case 128: return ws_fits<TP, 128>();
-    case 192: return ws_fits<TP, 192>();
-    case 256: return ws_fits<TP, 256>();
-    default: return false;
+WsPlan ws_plan(int dv) {
+  WsPlan pl;
+  for (int vs = 1; vs <= 4; vs *= 2) {
+    if (dv % vs) break;
+    const int t = dv / vs;
+    int r = 0;
+    switch (t) {
+      case 32: r = ws_rounds<TP, 32>(); break;
+      case 64: r = ws_rounds<TP, 64>(); break;
+      case 96: r = ws_rounds<TP, 96>(); break;
+      case 128: r = ws_rounds<TP, 128>(); break;
+      case 192: r = ws_rounds<TP, 192>(); break;
+      case 256: r = ws_rounds<TP, 256>(); break;
+      default: r = 0;
+    }
+    if (r) {
+      pl.dv_tile = t;
+      pl.rounds = r;
+      return pl;
+    }
+  }
+  return pl;
+}
+
+WsPlan ws_plan_for(int K, int dv) {
+  switch (ws_taps_pad(K)) {
+    case 16: return ws_plan<16>(dv);
+    case 32: return ws_plan<32>(dv);
+    case 64: return ws_plan<64>(dv);
+    case 96: return ws_plan<96>(dv);
+    case 128: return ws_plan<128>(dv);
+    default: return WsPlan{};
+  }
+}
+
+template <int TP, int DV>
+int launch_ws_rounds(const naf_xattn_params& p, int rounds, int vsplit, cudaStream_t st) {
+  switch (rounds) {
+    case 1: return launch_ws<TP, DV, 1>(p, vsplit, st);
+    case 2: if constexpr (DV % 64 == 0) return launch_ws<TP, DV, 2>(p, vsplit, st); break;
+    case 4: if constexpr (DV % 128 == 0) return launch_ws<TP, DV, 4>(p, vsplit, st); break;
+    default: break;
+  }
+  return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): bad plan");
+}
+
+template <int TP>
+int launch_ws_tp(const naf_xattn_params& p, cudaStream_t st) {
+  const int dv = p.C / p.heads;
+  const WsPlan pl = ws_plan<TP>(dv);
+  if (!pl.dv_tile) return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): no plan for dv=%d", dv);
+  const int vsplit = dv / pl.dv_tile;
+  switch (pl.dv_tile) {
+    case 32: return launch_ws_rounds<TP, 32>(p, pl.rounds, vsplit, st);
+    case 64: return launch_ws_rounds<TP, 64>(p, pl.rounds, vsplit, st);
+    case 96: return launch_ws_rounds<TP, 96>(p, pl.rounds, vsplit, st);
+    case 128: return launch_ws_rounds<TP, 128>(p, pl.rounds, vsplit, st);
+    case 192: return launch_ws_rounds<TP, 192>(p, pl.rounds, vsplit, st);
+    case 256: return launch_ws_rounds<TP, 256>(p, pl.rounds, vsplit, st);
+    default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): bad plan");
   }
 }
 
@@ -522,16 +658,9 @@ bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why) {
   if (p.scores) { *why = "score output requested"; return false; }
   if (dq != DQ) { *why = "head dim must be 64"; return false; }
   if (p.K < 3) { *why = "kernel_size must be 3, 5, 7, 9 or 11"; return false; }
-  bool fits = false;
-  switch (ws_taps_pad(p.K)) {
-    case 16: fits = ws_fits_dv<16>(dv); break;
-    case 32: fits = ws_fits_dv<32>(dv); break;
-    case 64: fits = ws_fits_dv<64>(dv); break;
-    case 96: fits = ws_fits_dv<96>(dv); break;
-    case 128: fits = ws_fits_dv<128>(dv); break;
-    default: break;
-  }
-  if (!fits) { *why = "window / value tile does not fit shared memory + TMEM of the pipelined kernel"; return false; }
+  if (dv % 32) { *why = "value head dim must be a multiple of 32"; return false; }
+  const WsPlan pl = ws_plan_for(p.K, dv);
+  if (!pl.dv_tile) { *why = "window / value tile does not fit shared memory + TMEM of the pipelined kernel"; return false; }
   if ((p.Ho / p.h) * (p.Wo / p.w) < 64) { *why = "fewer than 64 pixels per cell"; return false; }
   if (!aligned32(p.q) || !aligned32(p.k) || !aligned32(p.v) || !aligned32(p.out) ||
       (p.q_stride_b % 8) || (p.q_stride_y % 8) || (p.q_stride_x % 8)) {
@@ -542,17 +671,17 @@ bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why) {
     *why = "rope tables not 32-byte aligned";
     return false;
   }
-  if (int64_t(p.B) * p.h * p.w * p.heads >= (int64_t(1) << 31)) { *why = "too many items"; return false; }
+  if (int64_t(p.B) * p.h * p.w * p.heads * (dv / pl.dv_tile) >= (int64_t(1) << 31)) { *why = "too many items"; return false; }
   return true;
 }
 
 int launch_xattn_cell_tcws(const naf_xattn_params& p, cudaStream_t st) {
   switch (ws_taps_pad(p.K)) {
-    case 16: return launch_ws_dv<16>(p, st);
-    case 32: return launch_ws_dv<32>(p, st);
-    case 64: return launch_ws_dv<64>(p, st);
-    case 96: return launch_ws_dv<96>(p, st);
-    case 128: return launch_ws_dv<128>(p, st);
+    case 16: return launch_ws_tp<16>(p, st);
+    case 32: return launch_ws_tp<32>(p, st);
+    case 64: return launch_ws_tp<64>(p, st);
+    case 96: return launch_ws_tp<96>(p, st);
+    case 128: return launch_ws_tp<128>(p, st);
     default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): kernel_size %d", p.K);
   }
 }
