@@ -174,6 +174,43 @@ NAF_API int naf_gn_silu_apply_f32(const float* y, const float* bias, const float
                                   const float* beta, const double* sums, float* out, int B, int H,
                                   int W, int C, int G, float eps, int pad, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Guidance conv encoder on the tensor core: the whole `encoder()` stack of the
+ * reference (src/layers/convolutions.py:70-95; 128 channels, 8 groups, SiLU, reflect padding, no
+ * residual -- the NAF defaults, src/model/naf.py:26-27) with every activation crossing HBM twice
+ * per layer instead of five times.  Activations are pixel-major (B,H,W,128) fp32.
+ *
+ *   naf_enc_stem_f32      : nn.Conv2d(3, 128, KS, padding=KS/2, padding_mode="reflect") + bias on
+ *                           an image (B,3,H,W) of any element strides (convolutions.py:72-79);
+ *                           also emits per-tile partial sums {sum, sumsq} per GroupNorm group of
+ *                           its output: part (B, ceil(H/16)*ceil(W/8), 8, 2) fp32 (NULL: skipped).
+ *   naf_enc_gn_coef_f32   : nn.GroupNorm(8, 128, eps) statistics from those partial sums, reduced
+ *                           in double in a fixed order, folded with the affine parameters:
+ *                           coef (B,128,2) = { rstd*gamma, beta - mean*rstd*gamma } (biased var).
+ *   naf_enc_conv_pack_f32 : Conv2d weight (128,128,KS,KS) fp32 -> the fp16 hi/lo operand image the
+ *                           conv kernel streams: KS*KS*65536 bytes.
+ *   naf_enc_conv_f32      : EncBlock half  GroupNorm -> SiLU -> Conv2d(128,128,KS, reflect) + bias
+ *                           (convolutions.py:55-67): out = conv(silu(in*coef.scale + coef.shift)).
+ *                           `out` is a 128-channel slab [out_channel_offset, +128) of a pixel-major
+ *                           tensor with out_pix_stride floats per pixel (the last layer of each
+ *                           branch writes straight into the concatenated guidance map,
+ *                           src/model/naf.py:33).  `part` as for the stem (for the next GroupNorm).
+ *                           passes = 1: operands rounded to fp16 (10-bit mantissa: the precision
+ *                           class of the TF32 convolutions PyTorch runs by default, i.e. the
+ *                           reference with torch.backends.cudnn.allow_tf32 = True);
+ *                           passes = 3: split-fp16 (hi*hi + lo*hi + hi*lo), fp32-class accuracy
+ *                           (allow_tf32 = False).  KS = 1 or 3; H, W >= 2 when KS = 3.
+ * ---------------------------------------------------------------------------------------- */
+NAF_API int naf_enc_stem_f32(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
+                             int64_t stride_w, const float* weight, const float* bias, float* out,
+                             float* part, int B, int H, int W, int KS, void* stream);
+NAF_API int naf_enc_gn_coef_f32(const float* part, const float* gamma, const float* beta, float* coef,
+                                int B, int H, int W, float eps, void* stream);
+NAF_API int naf_enc_conv_pack_f32(const float* weight, void* packed, int KS, void* stream);
+NAF_API int naf_enc_conv_f32(const float* in, const float* coef, const void* wpacked, const float* bias,
+                             float* out, int64_t out_pix_stride, int out_channel_offset, float* part,
+                             int B, int H, int W, int KS, int passes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

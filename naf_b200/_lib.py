@@ -73,6 +73,12 @@ EXPORTS = {
     "naf_gn_stats_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_int, _fp]),
     "naf_gn_silu_apply_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_float, C.c_int, _fp]),
+    "naf_enc_stem_f32": (C.c_int, [_fp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "naf_enc_gn_coef_f32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
+    "naf_enc_conv_pack_f32": (C.c_int, [_fp, _fp, C.c_int, _fp]),
+    "naf_enc_conv_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, _fp]),
     "naf_xattn_dump_taps_i32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, _fp]),
 }

@@ -198,6 +198,40 @@ int naf_gn_silu_apply_f32(const float* y, const float* bias, const float* gamma,
                               static_cast<cudaStream_t>(stream));
 }
 
+int naf_enc_stem_f32(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
+                     int64_t stride_w, const float* weight, const float* bias, float* out, float* part,
+                     int B, int H, int W, int KS, void* stream) {
+  NAF_REQUIRE(image && weight && out, NAF_ERR_NULL, "enc_stem: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_stem: sizes must be positive");
+  return launch_enc_stem(image, stride_b, stride_c, stride_h, stride_w, weight, bias, out, part, B, H, W,
+                         KS, static_cast<cudaStream_t>(stream));
+}
+
+int naf_enc_gn_coef_f32(const float* part, const float* gamma, const float* beta, float* coef, int B,
+                        int H, int W, float eps, void* stream) {
+  NAF_REQUIRE(part && gamma && beta && coef, NAF_ERR_NULL, "enc_gn_coef: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_gn_coef: sizes must be positive");
+  return launch_enc_gn_coef(part, gamma, beta, coef, B, H, W, eps, static_cast<cudaStream_t>(stream));
+}
+
+int naf_enc_conv_pack_f32(const float* weight, void* packed, int KS, void* stream) {
+  NAF_REQUIRE(weight && packed, NAF_ERR_NULL, "enc_conv_pack: NULL pointer");
+  return launch_enc_conv_pack(weight, packed, KS, static_cast<cudaStream_t>(stream));
+}
+
+int naf_enc_conv_f32(const float* in, const float* coef, const void* wpacked, const float* bias,
+                     float* out, int64_t out_pix_stride, int out_channel_offset, float* part, int B,
+                     int H, int W, int KS, int passes, void* stream) {
+  NAF_REQUIRE(in && coef && wpacked && out, NAF_ERR_NULL, "enc_conv: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_conv: sizes must be positive");
+#ifndef NAF_WITH_TC
+  return fail(NAF_ERR_UNSUPPORTED, "enc_conv: library built without the tensor-core path");
+#else
+  return launch_enc_conv(in, coef, wpacked, bias, out, out_pix_stride, out_channel_offset, part, B, H, W,
+                         KS, passes, static_cast<cudaStream_t>(stream));
+#endif
+}
+
 int naf_xattn_dump_taps_i32(int32_t* idx_out, const int32_t* row_tap, const int32_t* col_tap,
                             int Ho, int Wo, int h, int w, int K, void* stream) {
   NAF_REQUIRE(idx_out, NAF_ERR_NULL, "dump_taps: NULL output");

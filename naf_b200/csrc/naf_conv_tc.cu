@@ -1,0 +1,503 @@
+// Guidance conv encoder on the 5th-gen tensor core.
+//
+// The reference's encoder (src/layers/convolutions.py:70-95) is a stem Conv2d(3 -> 128, k, reflect)
+// followed by EncBlocks  GroupNorm(8) -> SiLU -> Conv2d(128 -> 128, k, reflect)  x2  (k = 1 for the
+// "pixel" branch, 3 for the "semantic" branch; src/model/naf.py:26-27).  Run layer by layer every
+// activation (822 MB at 8x448x448x128 fp32) crosses HBM five times per GroupNorm+conv pair
+// (statistics read, normalise read + write, conv read + write).  Here it crosses twice:
+//
+//   stem_conv_kernel      image -> y0 (+bias), per-tile GroupNorm partial sums of y0
+//   gn_coef_kernel        partial sums -> per (image, channel) scale/shift  (deterministic, double)
+//   conv128_tc_kernel     y_in -> [scale/shift + SiLU + fp16 split, reflect halo, in shared memory]
+//                         -> implicit GEMM on tcgen05 (accumulator in TMEM) -> +bias -> y_out,
+//                         per-tile partial sums of y_out for the NEXT GroupNorm
+//
+// conv128_tc_kernel: persistent CTAs, one 16x8 pixel tile (M = 128) at a time.
+//   warps 0-7  workers : prologue (halo tile HBM -> GN affine -> SiLU -> fp16 -> smem, K-major
+//                        canonical layout [channel chunk][halo y][halo x][16 B]) and epilogue
+//                        (TMEM -> +bias -> statistics -> smem slab -> cp.async.bulk to HBM)
+//   warp 8     mma     : for each tap (dy,dx) the A operand is the SAME halo tile addressed through a
+//                        shifted descriptor (start += (dy*WX+dx)*16 B, 8-row-group stride = one halo
+//                        row): no im2col copy exists anywhere.  B = that tap's 128x128 weights.
+//   warp 9     loader  : streams the pre-packed fp16 weights of each tap from L2 into a 2-slot ring
+//                        with cp.async.bulk + mbarrier complete_tx.
+// PASSES = 1: operands rounded to fp16 (10-bit mantissa, the precision class of the TF32 convolution
+//             the reference runs by default on GPU: torch.backends.cudnn.allow_tf32 = True);
+//             two CTAs per SM so one tile's prologue/epilogue overlaps the other's MMAs.
+// PASSES = 3: fp16 hi/lo split of both operands, hi*hi + lo*hi + hi*lo with fp32 accumulation
+//             (~22 mantissa bits: the strict-fp32 class, allow_tf32 = False).
+#include "naf_common.cuh"
+#include "naf_umma.cuh"
+
+namespace naf {
+
+using namespace umma;
+
+namespace {
+
+constexpr int CC = 128;              // channels in == channels out
+constexpr int NCHUNK = CC / 8;       // 16-byte fp16 chunks per pixel
+constexpr int TH = 16, TW = 8;       // pixel tile: 16 rows x 8 columns = 128 MMA rows
+constexpr int NWORK = 256;
+constexpr int NTHREADS = NWORK + 64;
+constexpr int MMA_WARP = NWORK / 32, LOAD_WARP = MMA_WARP + 1;
+constexpr int W_PLANE = NCHUNK * CC * 16;   // one tap, one plane (hi or lo): 32 KB
+constexpr int STAGE_SLOT = 128 + 16;        // epilogue staging slot per worker thread (+ bank pad)
+
+template <int KS, int PASSES>
+struct ConvCfg {
+  static constexpr int HY = TH + KS - 1, WX = TW + KS - 1, HP = HY * WX;
+  static constexpr int CS = HP * 16 + 16;     // chunk stride; the 16 B pad spreads the 16 chunks over banks
+  static constexpr int NPLANE = PASSES == 1 ? 1 : 2;
+  static constexpr int A_PLANE = NCHUNK * CS;
+  static constexpr int STAGE = NWORK * STAGE_SLOT;
+  static constexpr int A_RAW = NPLANE * A_PLANE > STAGE ? NPLANE * A_PLANE : STAGE;
+  static constexpr int A_BYTES = (A_RAW + 127) / 128 * 128;
+  static constexpr int NT = KS * KS;
+  static constexpr int W_GRAN = NPLANE * W_PLANE;   // bytes per tap in the ring
+  static constexpr int NSLOT = NT == 1 ? 1 : 2;
+  static constexpr int SMEM = A_BYTES + NSLOT * W_GRAN;
+  static constexpr int CTAS_PER_SM = PASSES == 1 ? 2 : 1;
+};
+
+struct ConvParams {
+  const float* in;        // (B,H,W,128) contiguous
+  const float2* coef;     // (B,128) {scale, shift} of the GroupNorm applied to `in`
+  const uint8_t* wpack;   // [tap][plane hi|lo][chunk 16][n 128][8 x fp16]
+  const float* bias;      // (128) or NULL
+  float* out;             // pixel-major, out_pix_stride floats per pixel, channels [out_ch_off, +128)
+  float* part;            // NULL or (B, tiles_y*tiles_x, 8 groups, {sum, sumsq})
+  int64_t out_pix_stride;
+  int out_ch_off;
+  int B, H, W, tiles_y, tiles_x;
+};
+
+__device__ __forceinline__ int reflect_clamp(int i, int n) {
+  i = i < 0 ? -i : i;
+  i = i >= n ? 2 * n - 2 - i : i;
+  return i < 0 ? 0 : (i >= n ? n - 1 : i);   // only reached by halo pixels of ragged tiles
+}
+
+template <bool FAST>
+__device__ __forceinline__ float silu(float t) {
+  if constexpr (FAST) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * t));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+    return t * r;
+  } else {
+    return t / (1.f + expf(-t));
+  }
+}
+
+__device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+}  // namespace
+
+template <int KS, int PASSES>
+__global__ void __launch_bounds__(NTHREADS, ConvCfg<KS, PASSES>::CTAS_PER_SM)
+conv128_tc_kernel(ConvParams p) {
+  using Cfg = ConvCfg<KS, PASSES>;
+  constexpr int WX = Cfg::WX, HP = Cfg::HP, CS = Cfg::CS, NT = Cfg::NT;
+  constexpr bool kResident = NT == 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_a_full, bar_acc_full, bar_w_full[2], bar_w_free[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float2 s_coef[CC];
+  __shared__ float s_bias[CC];
+  __shared__ float s_part[8][8];
+
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + Cfg::A_BYTES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int total = p.B * tiles_per_img;
+
+  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, 128);
+  if (tid == 0) {
+    mbar_init(&bar_a_full, NWORK);
+    mbar_init(&bar_acc_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_w_full[s], 1);
+      mbar_init(&bar_w_free[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (tid < CC) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < MMA_WARP) {
+    // ================================================================================ WORKERS
+    const int chunk = tid & 15;           // this thread's 8 input channels (prologue)
+    const int px0 = tid >> 4;
+    const int row = (warp & 3) * 32 + lane, hf = warp >> 2;   // epilogue: TMEM lane, column half
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    uint8_t* my_stage = sA + tid * STAGE_SLOT;
+    int prev_tile = -1;
+    auto flush_part = [&]() {   // after a workers barrier: the partial sums of the previous tile
+      if (p.part && prev_tile >= 0 && tid < 16) {
+        const int g = tid >> 1, which = tid & 1, w0 = (g >> 2) * 4, gl = g & 3;
+        const float s = (s_part[w0][gl * 2 + which] + s_part[w0 + 1][gl * 2 + which]) +
+                        (s_part[w0 + 2][gl * 2 + which] + s_part[w0 + 3][gl * 2 + which]);
+        p.part[int64_t(prev_tile) * 16 + tid] = s;
+      }
+    };
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int y0 = ty * TH, x0 = tx * TW;
+      if (tid < CC) s_coef[tid] = p.coef[b * CC + tid];
+      named_bar_workers();   // staging + s_part of the previous tile are free, s_coef is loaded
+      flush_part();
+      // ---- prologue: halo tile -> GN affine -> SiLU -> fp16 (hi[, lo]) -> smem
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 c = s_coef[chunk * 8 + j];
+        sc[j] = c.x;
+        sh[j] = c.y;
+      }
+      const float* img = p.in + int64_t(b) * p.H * p.W * CC + chunk * 8;
+#pragma unroll 4
+      for (int px = px0; px < HP; px += 16) {
+        const int hy = px / WX, hx = px - hy * WX;
+        const int sy = reflect_clamp(y0 + hy - KS / 2, p.H), sx = reflect_clamp(x0 + hx - KS / 2, p.W);
+        float v[8];
+        ldg_stream8(img + (int64_t(sy) * p.W + sx) * CC, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu<PASSES == 1>(fmaf(v[j], sc[j], sh[j]));
+        uint4 hi, lo;
+        if constexpr (PASSES == 1) {
+          const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+          const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+          hi.x = *reinterpret_cast<const uint32_t*>(&h0);
+          hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+          hi.z = *reinterpret_cast<const uint32_t*>(&h2);
+          hi.w = *reinterpret_cast<const uint32_t*>(&h3);
+        } else {
+          split2_f16(v[0], v[1], hi.x, lo.x);
+          split2_f16(v[2], v[3], hi.y, lo.y);
+          split2_f16(v[4], v[5], hi.z, lo.z);
+          split2_f16(v[6], v[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(sA + Cfg::A_PLANE + chunk * CS + px * 16) = lo;
+        }
+        *reinterpret_cast<uint4*>(sA + chunk * CS + px * 16) = hi;
+      }
+      fence_proxy_async_smem();
+      fence_before_sync();          // orders this thread's TMEM reads of the previous tile
+      mbar_arrive(&bar_a_full);
+      // ---- epilogue
+      mbar_wait(&bar_acc_full, it & 1);
+      fence_after_sync();
+      const int y = y0 + (row >> 3), x = x0 + (row & 7);
+      const bool valid = y < p.H && x < p.W;
+      float* orow = p.out + ((int64_t(b) * p.H + y) * p.W + x) * p.out_pix_stride + p.out_ch_off + hf * 64;
+      float st[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st[j] = 0.f;
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_off + hf * 64 + rd * 32, r);
+        wait_ld();
+        bulk_wait_read<0>();   // the previous bulk store has finished reading this thread's slot
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int c = hf * 64 + rd * 32 + j;
+          float4 o;
+          o.x = __uint_as_float(r[j]) + s_bias[c];
+          o.y = __uint_as_float(r[j + 1]) + s_bias[c + 1];
+          o.z = __uint_as_float(r[j + 2]) + s_bias[c + 2];
+          o.w = __uint_as_float(r[j + 3]) + s_bias[c + 3];
+          const int g = rd * 2 + (j >> 4);
+          st[g * 2] += (o.x + o.y) + (o.z + o.w);
+          st[g * 2 + 1] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          *reinterpret_cast<float4*>(my_stage + j * 4) = o;
+        }
+        fence_proxy_async_smem();
+        if (valid) bulk_store(orow + rd * 32, my_stage, 128);
+        bulk_commit();
+      }
+      if (p.part) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = valid ? st[j] : 0.f;
+          v = warp_sum(v);
+          if (lane == 0) s_part[warp][j] = v;
+        }
+      }
+      bulk_wait_read<0>();
+      prev_tile = tile;
+    }
+    named_bar_workers();
+    flush_part();
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (warp == MMA_WARP) {
+    // ============================================================================= MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, CC, false, false);
+      const uint32_t a_base = smem_u32(sA), w_base = smem_u32(sW);
+      uint32_t n = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        mbar_wait(&bar_a_full, it & 1);
+        fence_after_sync();
+#pragma unroll 1
+        for (int tap = 0; tap < NT; ++tap, ++n) {
+          const int slot = kResident ? 0 : int(n & 1);
+          if (!kResident) mbar_wait(&bar_w_full[slot], (n >> 1) & 1);
+          else if (n == 0) mbar_wait(&bar_w_full[0], 0);
+          const int dy = tap / KS, dx = tap - dy * KS;
+          const uint32_t a_tap = a_base + (dy * WX + dx) * 16;
+          const uint32_t w_tap = w_base + slot * Cfg::W_GRAN;
+#pragma unroll
+          for (int pass = 0; pass < PASSES; ++pass) {
+            const uint32_t a0 = a_tap + (pass == 1 ? Cfg::A_PLANE : 0);
+            const uint32_t b0 = w_tap + (pass == 2 ? W_PLANE : 0);
+#pragma unroll
+            for (int kk = 0; kk < CC / 16; ++kk) {
+              const uint64_t da = make_desc(a0 + kk * 2 * CS, CS, WX * 16);
+              const uint64_t db = make_desc(b0 + kk * 2 * (CC * 16), CC * 16, 128);
+              mma_f16_ss(tmem, da, db, idesc, (tap | pass | kk) != 0);
+            }
+          }
+          if (!kResident) commit(&bar_w_free[slot]);
+        }
+        commit(&bar_acc_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================================= LOADER
+    if (lane == 0 && blockIdx.x < total) {
+      if (kResident) {
+        mbar_expect_tx(&bar_w_full[0], Cfg::W_GRAN);
+        bulk_load(sW, p.wpack, Cfg::W_GRAN, &bar_w_full[0]);
+      } else {
+        uint32_t n = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+#pragma unroll 1
+          for (int tap = 0; tap < NT; ++tap, ++n) {
+            const int slot = int(n & 1);
+            if (n >= 2) mbar_wait(&bar_w_free[slot], ((n >> 1) - 1) & 1);
+            mbar_expect_tx(&bar_w_full[slot], Cfg::W_GRAN);
+            bulk_load(sW + slot * Cfg::W_GRAN, p.wpack + size_t(tap) * 2 * W_PLANE, Cfg::W_GRAN,
+                      &bar_w_full[slot]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 128);
+}
+
+// ---- stem: Conv2d(3 -> 128, KS, reflect) + bias, pixel-major output, GroupNorm partial sums ------
+// One CTA (128 threads) per 16x8 tile; thread = 4 output channels (weights in registers) x 32 pixels;
+// the 3-channel halo tile sits in shared memory and is read with warp-wide broadcasts.
+template <int KS>
+__global__ void __launch_bounds__(128)
+stem_conv_kernel(const float* __restrict__ image, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+                 const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                 float* __restrict__ part, int H, int W, int tiles_x) {
+  constexpr int HY = TH + KS - 1, WX = TW + KS - 1, NK = 3 * KS * KS;
+  __shared__ __align__(16) float s_in[HY * WX][4];   // [halo pixel][channel (3) + pad]
+  __shared__ float s_red[4][8][2];
+  const int tid = threadIdx.x, q = tid & 31, slot = tid >> 5;
+  const int b = blockIdx.y, ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+  const int y0 = ty * TH, x0 = tx * TW;
+  for (int i = tid; i < HY * WX; i += 128) {
+    const int hy = i / WX, hx = i - hy * WX;
+    const int yy = reflect_clamp(y0 + hy - KS / 2, H), xx = reflect_clamp(x0 + hx - KS / 2, W);
+    const float* src = image + b * sb + yy * sy + xx * sx;
+    s_in[i][0] = src[0];
+    s_in[i][1] = src[sc];
+    s_in[i][2] = src[2 * sc];
+    s_in[i][3] = 0.f;
+  }
+  // weights (128, 3, KS, KS): wr[o][ (dy*KS+dx)*3 + ci ]
+  float wr[4][NK];
+#pragma unroll
+  for (int o = 0; o < 4; ++o)
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int t = 0; t < KS * KS; ++t) wr[o][t * 3 + ci] = w[((4 * q + o) * 3 + ci) * KS * KS + t];
+  const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  float s = 0.f, ss = 0.f;
+#pragma unroll 2
+  for (int pi = slot; pi < TH * TW; pi += 4) {
+    const int py = pi >> 3, pxx = pi & 7;
+    float4 acc = bv;
+#pragma unroll
+    for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < KS; ++dx) {
+        const float4 in = *reinterpret_cast<const float4*>(&s_in[(py + dy) * WX + pxx + dx][0]);
+        const int t = (dy * KS + dx) * 3;
+        acc.x = fmaf(in.x, wr[0][t], fmaf(in.y, wr[0][t + 1], fmaf(in.z, wr[0][t + 2], acc.x)));
+        acc.y = fmaf(in.x, wr[1][t], fmaf(in.y, wr[1][t + 1], fmaf(in.z, wr[1][t + 2], acc.y)));
+        acc.z = fmaf(in.x, wr[2][t], fmaf(in.y, wr[2][t + 1], fmaf(in.z, wr[2][t + 2], acc.z)));
+        acc.w = fmaf(in.x, wr[3][t], fmaf(in.y, wr[3][t + 1], fmaf(in.z, wr[3][t + 2], acc.w)));
+      }
+    const int y = y0 + py, x = x0 + pxx;
+    if (y < H && x < W) {
+      stg_stream(out + ((int64_t(b) * H + y) * W + x) * CC + 4 * q, acc);
+      s += (acc.x + acc.y) + (acc.z + acc.w);
+      ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+    }
+  }
+  if (part) {
+    // 4 adjacent lanes share a group (16 channels)
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    if ((q & 3) == 0) {
+      s_red[slot][q >> 2][0] = s;
+      s_red[slot][q >> 2][1] = ss;
+    }
+    __syncthreads();
+    if (tid < 16) {
+      const int g = tid >> 1, which = tid & 1;
+      const float v = (s_red[0][g][which] + s_red[1][g][which]) + (s_red[2][g][which] + s_red[3][g][which]);
+      part[(int64_t(b) * gridDim.x + blockIdx.x) * 16 + tid] = v;
+    }
+  }
+}
+
+// ---- GroupNorm coefficients from the per-tile partial sums (deterministic order, double) --------
+// coef[b][c] = { rstd*gamma[c], beta[c] - mean*rstd*gamma[c] }   (biased variance, torch GroupNorm)
+__global__ void __launch_bounds__(256)
+gn_coef_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float2* __restrict__ coef, int tiles, double count, float eps) {
+  __shared__ float s_mean[8], s_rstd[8];
+  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double ds = 0.0, dss = 0.0;
+  const float* base = part + int64_t(b) * tiles * 16 + g * 2;
+  for (int i = lane; i < tiles; i += 32) {
+    ds += double(base[int64_t(i) * 16]);
+    dss += double(base[int64_t(i) * 16 + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    dss += __shfl_xor_sync(0xffffffffu, dss, o);
+  }
+  if (lane == 0) {
+    const double mean = ds / count;
+    double var = dss / count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean[g] = float(mean);
+    s_rstd[g] = float(1.0 / sqrt(var + double(eps)));
+  }
+  __syncthreads();
+  if (threadIdx.x < CC) {
+    const int c = threadIdx.x;
+    const float a = s_rstd[c >> 4] * gamma[c];
+    coef[b * CC + c] = make_float2(a, beta[c] - s_mean[c >> 4] * a);
+  }
+}
+
+// ---- weight packing: (128,128,KS,KS) fp32 -> [tap][hi|lo][chunk][n][8] fp16 ----------------------
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __half* __restrict__ out, int KS) {
+  const int NT = KS * KS;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NT * CC * CC) return;
+  const int j = i & 7, n = (i >> 3) & 127, c = (i >> 10) & 15, tap = i >> 14;
+  const float v = w[(int64_t(n) * CC + c * 8 + j) * NT + tap];
+  const __half hi = __float2half_rn(v);
+  const __half lo = __float2half_rn(v - __half2float(hi));
+  const int64_t o = (int64_t(tap) * 2 * NCHUNK + c) * (CC * 8) + n * 8 + j;
+  out[o] = hi;
+  out[o + int64_t(NCHUNK) * CC * 8] = lo;
+}
+
+// ------------------------------------------------------------------------------------ host side
+namespace {
+
+template <int KS, int PASSES>
+int launch_conv(const ConvParams& p, cudaStream_t st) {
+  using Cfg = ConvCfg<KS, PASSES>;
+  auto kern = conv128_tc_kernel<KS, PASSES>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t total = int64_t(p.B) * p.tiles_y * p.tiles_x;
+  const int64_t cap = int64_t(sms) * Cfg::CTAS_PER_SM;
+  const int grid = int(total < cap ? total : cap);
+  kern<<<grid, NTHREADS, Cfg::SMEM, st>>>(p);
+  return check_launch("enc_conv");
+}
+
+}  // namespace
+
+int launch_enc_conv(const float* in, const float* coef, const void* wpack, const float* bias, float* out,
+                    int64_t out_pix_stride, int out_ch_off, float* part, int B, int H, int W, int KS,
+                    int passes, cudaStream_t st) {
+  NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_conv: kernel size %d (1 or 3)", KS);
+  NAF_REQUIRE(passes == 1 || passes == 3, NAF_ERR_UNSUPPORTED, "enc_conv: passes must be 1 or 3");
+  NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_conv: reflect padding needs H, W >= 2");
+  NAF_REQUIRE(aligned32(in) && aligned16(wpack) && aligned16(out) && aligned16(coef) &&
+                  out_pix_stride % 4 == 0 && out_ch_off % 4 == 0 && out_pix_stride >= out_ch_off + CC,
+              NAF_ERR_ALIGNMENT, "enc_conv: alignment / output slab");
+  NAF_REQUIRE(int64_t(B) * ((H + TH - 1) / TH) * ((W + TW - 1) / TW) < (int64_t(1) << 27), NAF_ERR_UNSUPPORTED,
+              "enc_conv: too many tiles");
+  ConvParams p;
+  p.in = in;
+  p.coef = reinterpret_cast<const float2*>(coef);
+  p.wpack = static_cast<const uint8_t*>(wpack);
+  p.bias = bias;
+  p.out = out;
+  p.part = part;
+  p.out_pix_stride = out_pix_stride;
+  p.out_ch_off = out_ch_off;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.tiles_y = (H + TH - 1) / TH;
+  p.tiles_x = (W + TW - 1) / TW;
+  if (KS == 1) return passes == 1 ? launch_conv<1, 1>(p, st) : launch_conv<1, 3>(p, st);
+  return passes == 1 ? launch_conv<3, 1>(p, st) : launch_conv<3, 3>(p, st);
+}
+
+int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
+                    const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st) {
+  NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_stem: kernel size %d (1 or 3)", KS);
+  NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_stem: reflect padding needs H, W >= 2");
+  NAF_REQUIRE(aligned16(out) && (!bias || aligned16(bias)), NAF_ERR_ALIGNMENT, "enc_stem: 16-byte alignment");
+  NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "enc_stem: batch too large");
+  const int tiles_y = (H + TH - 1) / TH, tiles_x = (W + TW - 1) / TW;
+  const dim3 grid(unsigned(tiles_y * tiles_x), unsigned(B), 1u);
+  if (KS == 1) stem_conv_kernel<1><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x);
+  else stem_conv_kernel<3><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x);
+  return check_launch("enc_stem");
+}
+
+int launch_enc_gn_coef(const float* part, const float* gamma, const float* beta, float* coef, int B, int H,
+                       int W, float eps, cudaStream_t st) {
+  NAF_REQUIRE(aligned16(coef), NAF_ERR_ALIGNMENT, "enc_gn_coef: 16-byte alignment");
+  const int tiles = ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
+  gn_coef_kernel<<<B, 256, 0, st>>>(part, gamma, beta, reinterpret_cast<float2*>(coef), tiles,
+                                    double(H) * W * 16.0, eps);
+  return check_launch("enc_gn_coef");
+}
+
+int launch_enc_conv_pack(const float* w, void* packed, int KS, cudaStream_t st) {
+  NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_conv_pack: kernel size %d (1 or 3)", KS);
+  const int n = KS * KS * CC * CC;
+  pack_conv_w_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, static_cast<__half*>(packed), KS);
+  return check_launch("enc_conv_pack");
+}
+
+}  // namespace naf

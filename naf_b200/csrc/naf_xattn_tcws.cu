@@ -70,10 +70,6 @@ __device__ __forceinline__ void ws_split8(const float* x, uint4& hi, uint4& lo) 
   split2_f16(x[6], x[7], hi.w, lo.w);
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
-}
-
 // Division by a launch-constant divisor as multiply-high + shift (exact for the small operands
 // used here: n < 2^31 / d, d <= 2^15); the table lives in the kernel parameter constant bank, so
 // the per-tile index arithmetic of 272 threads costs no registers and ~3 instructions per divide.

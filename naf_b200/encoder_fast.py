@@ -84,6 +84,99 @@ def groupnorm_silu(y, prev_bias, norm, pad: int):
     return out
 
 
+# ------------------------------------------------------------------------ tensor-core encoder
+TILE_H, TILE_W = 16, 8   # pixel tile of the conv kernels (naf_conv_tc.cu)
+
+
+def tc_supported(seq) -> bool:
+    """The fused tensor-core stack handles exactly the NAF default branch: 3 -> 128 stem, EncBlocks
+    of 128 channels with GroupNorm(8), SiLU, bias, reflect padding, one kernel size (1 or 3)."""
+    if not supported(seq) or not _lib.load().naf_has_tensor_path():
+        return False
+    stem = seq[0]
+    k = stem.kernel_size[0]
+    if stem.in_channels != 3 or stem.out_channels != 128 or stem.bias is None:
+        return False
+    for blk in list(seq)[1:]:
+        for norm, conv in ((blk.norm1, blk.conv1), (blk.norm2, blk.conv2)):
+            if (norm.num_channels != 128 or norm.num_groups != 8 or conv.out_channels != 128
+                    or conv.kernel_size[0] != k or conv.bias is None):
+                return False
+    return True
+
+
+def conv_passes() -> int:
+    """1 = fp16-rounded operands (the precision class of PyTorch's default TF32 convolutions),
+    3 = split-fp16 with fp32-class accuracy; follows `torch.backends.cudnn.allow_tf32` like the
+    reference's own convolutions do."""
+    return 1 if torch.backends.cudnn.allow_tf32 else 3
+
+
+def _packed_weight(conv):
+    """fp16 hi/lo operand image of a 128x128xKxK conv weight (naf_enc_conv_pack_f32), cached."""
+    w = conv.weight
+    key = (w.data_ptr(), w._version, w.device)
+    cache = getattr(conv, "_naf_wtc", None)
+    if cache is None or cache[0] != key:
+        k = conv.kernel_size[0]
+        packed = torch.empty(k * k * 65536, device=w.device, dtype=torch.uint8)
+        wc = w.detach().float().contiguous()
+        with torch.cuda.device(w.device):
+            rc = _lib.load().naf_enc_conv_pack_f32(ops._ptr(wc), ops._ptr(packed), k, ops._stream(w.device))
+        _lib.check(rc, "naf_enc_conv_pack_f32")
+        cache = (key, packed)
+        conv._naf_wtc = cache
+    return cache[1]
+
+
+def forward_tc(seq, image, out=None, ch_off=0, passes=None):
+    """`seq(image)` on our kernels only: stem conv, then per EncBlock half one tiny coefficient
+    kernel and ONE fused GroupNorm+SiLU+conv kernel.  Returns the pixel-major (B,H,W,C_total)
+    tensor `out` whose channels [ch_off, ch_off+128) hold the result (bias included); `out` is
+    allocated (128 channels) when not given."""
+    lib = _lib.load()
+    dev = image.device
+    x = image if image.dtype == torch.float32 else image.float()
+    B, _, H, W = x.shape
+    passes = conv_passes() if passes is None else int(passes)
+    stem = seq[0]
+    k = stem.kernel_size[0]
+    tiles = -(-H // TILE_H) * -(-W // TILE_W)
+    st = ops._stream(dev)
+    layers = [(n, c) for blk in list(seq)[1:] for n, c in ((blk.norm1, blk.conv1), (blk.norm2, blk.conv2))]
+    if out is None:
+        out = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
+        ch_off = 0
+    assert out.is_contiguous() and tuple(out.shape[:3]) == (B, H, W)
+    pix_stride = out.shape[-1]
+    part = torch.empty((B, tiles, 16), device=dev, dtype=torch.float32)
+    coef = torch.empty((B, 128, 2), device=dev, dtype=torch.float32)
+    bufs = [torch.empty((B, H, W, 128), device=dev, dtype=torch.float32) for _ in range(min(2, len(layers)))]
+    sb, sc, sy, sx = x.stride()
+    with torch.cuda.device(dev):
+        last = len(layers) == 0
+        y = out if last else bufs[0]
+        rc = lib.naf_enc_stem_f32(ops._ptr(x), sb, sc, sy, sx, ops._ptr(stem.weight), ops._ptr(stem.bias),
+                                  ops._ptr(y), ops._ptr(None if last else part), B, H, W, k, st)
+        _lib.check(rc, "naf_enc_stem_f32")
+        if last and (pix_stride != 128 or ch_off):
+            raise NotImplementedError("stem-only encoder into a slab")
+        for i, (norm, conv) in enumerate(layers):
+            last = i == len(layers) - 1
+            rc = lib.naf_enc_gn_coef_f32(ops._ptr(part), ops._ptr(norm.weight), ops._ptr(norm.bias),
+                                         ops._ptr(coef), B, H, W, float(norm.eps), st)
+            _lib.check(rc, "naf_enc_gn_coef_f32")
+            dst = out if last else bufs[(i + 1) & 1]
+            rc = lib.naf_enc_conv_f32(ops._ptr(y), ops._ptr(coef), ops._ptr(_packed_weight(conv)),
+                                      ops._ptr(conv.bias), ops._ptr(dst), pix_stride if last else 128,
+                                      ch_off if last else 0, ops._ptr(None if last else part), B, H, W, k,
+                                      passes, st)
+            _lib.check(rc, "naf_enc_conv_f32")
+            y = dst
+    ops.LAUNCHES["encoder_tc"] = ops.LAUNCHES.get("encoder_tc", 0) + 1 + 2 * len(layers)
+    return out
+
+
 def forward(seq, image):
     """Pixel-major (B,H,W,C) output of `seq(image)` WITHOUT the bias of the last convolution, and
     that bias (or None): the caller folds it into the concat pass."""

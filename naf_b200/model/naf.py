@@ -30,6 +30,7 @@ class ImageEncoder(nn.Module):
         self.use_encoder = use_encoder
         self.out_channels = out_channels
         self.fast_encoder = True   # False: run the conv stacks as plain torch modules
+        self.tc_encoder = True     # False: cuDNN convolutions between our GroupNorm kernels
         half = out_channels // 2
         self.encoder = encoder(in_channels, half, kernel_size=1, ks_res=1, num_layers=img_layers)
         self.sem_encoder = encoder(in_channels, half, kernel_size=3, ks_res=3, num_layers=img_layers)
@@ -76,6 +77,15 @@ class ImageEncoder(nn.Module):
         Hs, Ws = image.shape[-2:]
         if not (image.is_cuda and self.use_encoder and Ho % Hs == 0 and Wo % Ws == 0):
             return self.forward_encoder(image, (Ho, Wo)), (1, 1)
+        if (self.fast_encoder and self.tc_encoder and encoder_fast.tc_supported(self.encoder)
+                and encoder_fast.tc_supported(self.sem_encoder) and Hs >= 2 and Ws >= 2):
+            # whole conv stack on our tcgen05 kernels; both branches write their 128-channel slab
+            # of the concatenated guidance map directly (no torch.cat pass)
+            B = image.shape[0]
+            x = torch.empty((B, Hs, Ws, 2 * 128), device=image.device, dtype=torch.float32)
+            encoder_fast.forward_tc(self.encoder, image, out=x, ch_off=0)
+            encoder_fast.forward_tc(self.sem_encoder, image, out=x, ch_off=128)
+            return x.permute(0, 3, 1, 2), (Ho // Hs, Wo // Ws)
         if (self.fast_encoder and image.dtype == torch.float32 and encoder_fast.supported(self.encoder)
                 and encoder_fast.supported(self.sem_encoder)):
             # our GroupNorm/SiLU/pad kernels between cuDNN convs, pixel-major end to end

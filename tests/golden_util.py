@@ -50,3 +50,17 @@ def module_case(name):
 def module_state():
     d = np.load(os.path.join(GOLDEN, "naf_dim128_k7_state.npz"))
     return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+# ---- default-width model (dim=256: the shape the tensor-core encoder implements) --------------
+def default_case(name):
+    d = load(name)
+    seed = int(d["seed"])
+    return dict(image=seeded_normal(seed, d["image_shape"]), features=seeded_normal(seed + 1, d["features_shape"]),
+                out=torch.from_numpy(d["out"]), queries_sub=torch.from_numpy(d["queries_sub"]),
+                qstep=int(d["qstep"]), output_size=tuple(int(x) for x in d["output_size"]))
+
+
+def default_state():
+    d = np.load(os.path.join(GOLDEN, "naf256_k7_state.npz"))
+    return {k: torch.from_numpy(d[k]) for k in d.files}

@@ -86,3 +86,18 @@ def test_training_mode_augmentation_is_refused():
     with pytest.raises(NotImplementedError):
         rope.axis_tables(4, 4)
     rope.eval().axis_tables(4, 4)
+
+
+def test_default_width_encoder_on_cpu_plus_oracle_matches_reference_golden():
+    """Module tree (torch CPU) + oracle tail == the unmodified reference at the default width
+    (dim=256), the fixtures the tensor-core encoder is held to on the GPU."""
+    from oracle import naf_oracle as O
+
+    m = naf_b200.NAF(kernel_size=7).eval()
+    m.load_state_dict(G.default_state(), strict=True)
+    for name in G.names("naf256_"):
+        c = G.default_case(name)
+        with torch.no_grad():
+            x = m.image_encoder.guidance(c["image"], c["output_size"])
+        out = O.naf_forward(x.contiguous(), c["features"], 4, 4, 7)
+        assert (out - c["out"]).abs().max().item() <= 2e-5, name
