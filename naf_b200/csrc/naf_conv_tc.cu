@@ -15,7 +15,7 @@
 // conv128_tc_kernel: persistent CTAs, one 16x8 pixel tile (M = 128) at a time.
 //   warps 0-7  workers : prologue (halo tile HBM -> GN affine -> SiLU -> fp16 -> smem, K-major
 //                        canonical layout [channel chunk][halo y][halo x][16 B]) and epilogue
-//                        (TMEM -> +bias -> statistics -> smem slab -> cp.async.bulk to HBM)
+//                        (TMEM -> +bias -> statistics -> per-warp smem transpose -> 128-byte-run stores)
 //   warp 8     mma     : for each tap (dy,dx) the A operand is the SAME halo tile addressed through a
 //                        shifted descriptor (start += (dy*WX+dx)*16 B, 8-row-group stride = one halo
 //                        row): no im2col copy exists anywhere.  B = that tap's 128x128 weights.
@@ -28,6 +28,10 @@
 //             (~22 mantissa bits: the strict-fp32 class, allow_tf32 = False).
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
+
+#ifndef NAF_CONV_EXP
+#define NAF_CONV_EXP 0   // profiling variants (scripts/conv_experiments.sh): 1 no output stores,
+#endif                   // 2 no input loads, 4 no MMAs, 8 weights loaded once, 16 no SiLU
 
 namespace naf {
 
@@ -136,6 +140,7 @@ conv128_tc_kernel(ConvParams p) {
     const int row = (warp & 3) * 32 + lane, hf = warp >> 2;   // epilogue: TMEM lane, column half
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     uint8_t* my_stage = sA + tid * STAGE_SLOT;
+    const uint8_t* warp_stage = sA + warp * 32 * STAGE_SLOT;
     int prev_tile = -1;
     auto flush_part = [&]() {   // after a workers barrier: the partial sums of the previous tile
       if (p.part && prev_tile >= 0 && tid < 16) {
@@ -167,9 +172,19 @@ conv128_tc_kernel(ConvParams p) {
         const int hy = px / WX, hx = px - hy * WX;
         const int sy = reflect_clamp(y0 + hy - KS / 2, p.H), sx = reflect_clamp(x0 + hx - KS / 2, p.W);
         float v[8];
+#if NAF_CONV_EXP & 2
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = float(sy + sx + j);
+#else
         ldg_stream8(img + (int64_t(sy) * p.W + sx) * CC, v);
+#endif
+#if NAF_CONV_EXP & 16
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+#else
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = silu<PASSES == 1>(fmaf(v[j], sc[j], sh[j]));
+#endif
         uint4 hi, lo;
         if constexpr (PASSES == 1) {
           const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
@@ -193,9 +208,14 @@ conv128_tc_kernel(ConvParams p) {
       // ---- epilogue
       mbar_wait(&bar_acc_full, it & 1);
       fence_after_sync();
-      const int y = y0 + (row >> 3), x = x0 + (row & 7);
-      const bool valid = y < p.H && x < p.W;
-      float* orow = p.out + ((int64_t(b) * p.H + y) * p.W + x) * p.out_pix_stride + p.out_ch_off + hf * 64;
+      // Each warp owns 32 TMEM lanes (pixels) x one 64-column half.  Per round of 32 columns the
+      // warp transposes through its private smem slab so that every store instruction writes four
+      // 128-byte runs (4 pixels x 32 channels) instead of 32 scattered 16-byte pieces.
+      const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
+      const int sub = lane >> 3, piece = lane & 7;
+      const int ybase = y0 + (warp & 3) * 4, xbase = x0 + sub;
+      float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off +
+                     hf * 64 + piece * 4;
       float st[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) st[j] = 0.f;
@@ -204,7 +224,7 @@ conv128_tc_kernel(ConvParams p) {
         uint32_t r[32];
         tmem_ld32(tmem + lane_off + hf * 64 + rd * 32, r);
         wait_ld();
-        bulk_wait_read<0>();   // the previous bulk store has finished reading this thread's slot
+        __syncwarp();   // the previous round's read-back of the slab is complete
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           const int c = hf * 64 + rd * 32 + j;
@@ -218,9 +238,14 @@ conv128_tc_kernel(ConvParams p) {
           st[g * 2 + 1] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
           *reinterpret_cast<float4*>(my_stage + j * 4) = o;
         }
-        fence_proxy_async_smem();
-        if (valid) bulk_store(orow + rd * 32, my_stage, 128);
-        bulk_commit();
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 o = *reinterpret_cast<const float4*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 16);
+          const int yy = ybase + (i >> 1), xx = xbase + (i & 1) * 4;
+          if (yy < p.H && xx < p.W && !(NAF_CONV_EXP & 1))
+            stg_stream(obase + (int64_t(i >> 1) * p.W + (i & 1) * 4) * p.out_pix_stride + rd * 32, o);
+        }
       }
       if (p.part) {
 #pragma unroll
@@ -230,12 +255,10 @@ conv128_tc_kernel(ConvParams p) {
           if (lane == 0) s_part[warp][j] = v;
         }
       }
-      bulk_wait_read<0>();
       prev_tile = tile;
     }
     named_bar_workers();
     flush_part();
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == MMA_WARP) {
     // ============================================================================= MMA ISSUER
     if (lane == 0) {
@@ -249,8 +272,12 @@ conv128_tc_kernel(ConvParams p) {
 #pragma unroll 1
         for (int tap = 0; tap < NT; ++tap, ++n) {
           const int slot = kResident ? 0 : int(n & 1);
+#if NAF_CONV_EXP & 8
+          if (n < 2) mbar_wait(&bar_w_full[slot], 0);
+#else
           if (!kResident) mbar_wait(&bar_w_full[slot], (n >> 1) & 1);
           else if (n == 0) mbar_wait(&bar_w_full[0], 0);
+#endif
           const int dy = tap / KS, dx = tap - dy * KS;
           const uint32_t a_tap = a_base + (dy * WX + dx) * 16;
           const uint32_t w_tap = w_base + slot * Cfg::W_GRAN;
@@ -262,10 +289,10 @@ conv128_tc_kernel(ConvParams p) {
             for (int kk = 0; kk < CC / 16; ++kk) {
               const uint64_t da = make_desc(a0 + kk * 2 * CS, CS, WX * 16);
               const uint64_t db = make_desc(b0 + kk * 2 * (CC * 16), CC * 16, 128);
-              mma_f16_ss(tmem, da, db, idesc, (tap | pass | kk) != 0);
+              if (!(NAF_CONV_EXP & 4)) mma_f16_ss(tmem, da, db, idesc, (tap | pass | kk) != 0);
             }
           }
-          if (!kResident) commit(&bar_w_free[slot]);
+          if (!kResident && !(NAF_CONV_EXP & 8)) commit(&bar_w_free[slot]);
         }
         commit(&bar_acc_full);
       }
@@ -274,6 +301,267 @@ conv128_tc_kernel(ConvParams p) {
   } else {
     // ================================================================================= LOADER
     if (lane == 0 && blockIdx.x < total) {
+      if (kResident) {
+        mbar_expect_tx(&bar_w_full[0], Cfg::W_GRAN);
+        bulk_load(sW, p.wpack, Cfg::W_GRAN, &bar_w_full[0]);
+      } else {
+        uint32_t n = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+#pragma unroll 1
+          for (int tap = 0; tap < NT; ++tap, ++n) {
+            const int slot = int(n & 1);
+#if NAF_CONV_EXP & 8
+            if (n >= 2) break;
+#endif
+            if (n >= 2) mbar_wait(&bar_w_free[slot], ((n >> 1) - 1) & 1);
+            mbar_expect_tx(&bar_w_full[slot], Cfg::W_GRAN);
+            bulk_load(sW + slot * Cfg::W_GRAN, p.wpack + size_t(tap) * 2 * W_PLANE, Cfg::W_GRAN,
+                      &bar_w_full[slot]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 128);
+}
+
+// ---- pipelined variant (1 pass): producer / MMA / epilogue warps work on different tiles ---------
+// One persistent CTA per SM.  A (the activated halo tile) and the TMEM accumulator are double
+// buffered, so at any time the 8 producer warps convert tile t+1 while the tensor core runs tile t
+// and the 8 epilogue warps drain tile t-1:
+//   warps 0-7   producers : halo tile HBM -> GN affine -> SiLU -> fp16 -> sA[t & 1]; L2 prefetch of
+//                           the tile after next
+//   warps 8-15  epilogue  : TMEM acc[t & 1] -> +bias -> statistics -> per-warp transpose -> stores
+//   warp 16     mma       : 9 (or 1) taps x 8 k-steps of tcgen05.mma per tile
+//   warp 17     loader    : weight ring, as above
+namespace {
+constexpr int WS_THREADS = 2 * NWORK + 64;
+constexpr int WS_MMA_WARP = 2 * NWORK / 32;
+
+template <int KS>
+struct WsConvCfg {
+  using Base = ConvCfg<KS, 1>;
+  static constexpr int A_BUF = (Base::A_PLANE + 127) / 128 * 128;
+  static constexpr int STAGE = NWORK * STAGE_SLOT;
+  static constexpr int W_OFF = 2 * A_BUF;
+  static constexpr int STAGE_OFF = W_OFF + Base::NSLOT * Base::W_GRAN;
+  static constexpr int SMEM = STAGE_OFF + STAGE;
+};
+}  // namespace
+
+template <int KS>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+conv128_ws_kernel(ConvParams p) {
+  using Cfg = ConvCfg<KS, 1>;
+  using Ws = WsConvCfg<KS>;
+  constexpr int WX = Cfg::WX, HP = Cfg::HP, CS = Cfg::CS, NT = Cfg::NT;
+  constexpr bool kResident = NT == 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_a_full[2], bar_a_free[2], bar_acc_full[2], bar_acc_free[2], bar_w_full[2], bar_w_free[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[CC];
+  __shared__ float s_part[2][8][8];
+
+  uint8_t* sW = smem + Ws::W_OFF;
+  uint8_t* sStage = smem + Ws::STAGE_OFF;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int total = p.B * tiles_per_img;
+
+  if (warp == WS_MMA_WARP) tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_a_full[s], NWORK);
+      mbar_init(&bar_a_free[s], 1);
+      mbar_init(&bar_acc_full[s], 1);
+      mbar_init(&bar_acc_free[s], NWORK);
+      mbar_init(&bar_w_full[s], 1);
+      mbar_init(&bar_w_free[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (tid < CC) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < 8) {
+    // ============================================================================== PRODUCERS
+    const int chunk = tid & 15, px0 = tid >> 4;
+    float sc[8], sh[8];
+    int b_cur = -1, it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int y0 = ty * TH, x0 = tx * TW;
+      if (b != b_cur) {   // GroupNorm scale/shift of this thread's 8 channels for image b
+        b_cur = b;
+        const float4* cp = reinterpret_cast<const float4*>(p.coef + b * CC + chunk * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 c = __ldg(cp + j);
+          sc[2 * j] = c.x;
+          sh[2 * j] = c.y;
+          sc[2 * j + 1] = c.z;
+          sh[2 * j + 1] = c.w;
+        }
+      }
+      {   // L2 prefetch of the tile after next (one 128-byte line per 4 chunks)
+        const int t2 = tile + 2 * gridDim.x;
+        if (t2 < total && (chunk & 3) == 0) {
+          const int b2 = t2 / tiles_per_img, rem2 = t2 - b2 * tiles_per_img;
+          const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
+          const float* img2 = p.in + int64_t(b2) * p.H * p.W * CC + chunk * 8;
+          for (int px = px0; px < HP; px += 16) {
+            const int hy = px / WX, hx = px - hy * WX;
+            const int sy = reflect_clamp(ty2 * TH + hy - KS / 2, p.H), sx = reflect_clamp(tx2 * TW + hx - KS / 2, p.W);
+            prefetch_l2(img2 + (int64_t(sy) * p.W + sx) * CC);
+          }
+        }
+      }
+      if (it >= 2) mbar_wait(&bar_a_free[buf], ((it >> 1) - 1) & 1);
+      uint8_t* sA = smem + buf * Ws::A_BUF;
+      const float* img = p.in + int64_t(b) * p.H * p.W * CC + chunk * 8;
+#pragma unroll 4
+      for (int px = px0; px < HP; px += 16) {
+        const int hy = px / WX, hx = px - hy * WX;
+        const int sy = reflect_clamp(y0 + hy - KS / 2, p.H), sx = reflect_clamp(x0 + hx - KS / 2, p.W);
+        float v[8];
+#if NAF_CONV_EXP & 2
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = float(sy + sx + j);
+#else
+        ldg_stream8(img + (int64_t(sy) * p.W + sx) * CC, v);
+#endif
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = silu<true>(fmaf(v[j], sc[j], sh[j]));
+        const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+        const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+        uint4 hi;
+        hi.x = *reinterpret_cast<const uint32_t*>(&h0);
+        hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+        hi.z = *reinterpret_cast<const uint32_t*>(&h2);
+        hi.w = *reinterpret_cast<const uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(sA + chunk * CS + px * 16) = hi;
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_a_full[buf]);
+    }
+  } else if (warp < 16) {
+    // =============================================================================== EPILOGUE
+    const int ew = warp - 8, et = tid - NWORK;
+    const int row = (ew & 3) * 32 + lane, hf = ew >> 2;
+    const uint32_t lane_off = uint32_t((ew & 3) * 32) << 16;
+    uint8_t* my_stage = sStage + et * STAGE_SLOT;
+    const uint8_t* warp_stage = sStage + ew * 32 * STAGE_SLOT;
+    const int sub = lane >> 3, piece = lane & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int y0 = ty * TH, x0 = tx * TW;
+      const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
+      const int ybase = y0 + (ew & 3) * 4, xbase = x0 + sub;
+      float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off +
+                     hf * 64 + piece * 4;
+      mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
+      fence_after_sync();
+      float st[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) st[j] = 0.f;
+#pragma unroll
+      for (int rd = 0; rd < 2; ++rd) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_off + buf * CC + hf * 64 + rd * 32, r);
+        wait_ld();
+        if (rd == 1) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
+          fence_before_sync();
+          mbar_arrive(&bar_acc_free[buf]);
+        }
+        __syncwarp();   // the previous round's read-back of the slab is complete
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int c = hf * 64 + rd * 32 + j;
+          float4 o;
+          o.x = __uint_as_float(r[j]) + s_bias[c];
+          o.y = __uint_as_float(r[j + 1]) + s_bias[c + 1];
+          o.z = __uint_as_float(r[j + 2]) + s_bias[c + 2];
+          o.w = __uint_as_float(r[j + 3]) + s_bias[c + 3];
+          const int g = rd * 2 + (j >> 4);
+          st[g * 2] += (o.x + o.y) + (o.z + o.w);
+          st[g * 2 + 1] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
+          *reinterpret_cast<float4*>(my_stage + j * 4) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 o = *reinterpret_cast<const float4*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 16);
+          const int yy = ybase + (i >> 1), xx = xbase + (i & 1) * 4;
+          if (yy < p.H && xx < p.W && !(NAF_CONV_EXP & 1))
+            stg_stream(obase + (int64_t(i >> 1) * p.W + (i & 1) * 4) * p.out_pix_stride + rd * 32, o);
+        }
+      }
+      if (p.part) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = valid ? st[j] : 0.f;
+          v = warp_sum(v);
+          if (lane == 0) s_part[buf][ew][j] = v;
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (et < 16) {
+          const int g = et >> 1, which = et & 1, w0 = (g >> 2) * 4, gl = g & 3;
+          const float s = (s_part[buf][w0][gl * 2 + which] + s_part[buf][w0 + 1][gl * 2 + which]) +
+                          (s_part[buf][w0 + 2][gl * 2 + which] + s_part[buf][w0 + 3][gl * 2 + which]);
+          p.part[int64_t(tile) * 16 + et] = s;
+        }
+      }
+    }
+  } else if (warp == WS_MMA_WARP) {
+    // ============================================================================= MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, CC, false, false);
+      const uint32_t w_base = smem_u32(sW);
+      uint32_t n = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bar_a_full[buf], (it >> 1) & 1);
+        if (it >= 2) mbar_wait(&bar_acc_free[buf], ((it >> 1) - 1) & 1);
+        fence_after_sync();
+        const uint32_t a_base = smem_u32(smem + buf * Ws::A_BUF);
+        const uint32_t tD = tmem + buf * CC;
+#pragma unroll 1
+        for (int tap = 0; tap < NT; ++tap, ++n) {
+          const int slot = kResident ? 0 : int(n & 1);
+          if (!kResident) mbar_wait(&bar_w_full[slot], (n >> 1) & 1);
+          else if (n == 0) mbar_wait(&bar_w_full[0], 0);
+          const int dy = tap / KS, dx = tap - dy * KS;
+          const uint32_t a0 = a_base + (dy * WX + dx) * 16;
+          const uint32_t b0 = w_base + slot * Cfg::W_GRAN;
+#pragma unroll
+          for (int kk = 0; kk < CC / 16; ++kk) {
+            const uint64_t da = make_desc(a0 + kk * 2 * CS, CS, WX * 16);
+            const uint64_t db = make_desc(b0 + kk * 2 * (CC * 16), CC * 16, 128);
+            if (!(NAF_CONV_EXP & 4)) mma_f16_ss(tD, da, db, idesc, (tap | kk) != 0);
+          }
+          if (!kResident) commit(&bar_w_free[slot]);
+        }
+        commit(&bar_a_free[buf]);
+        commit(&bar_acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================================= LOADER
+    if (lane == 0) {
       if (kResident) {
         mbar_expect_tx(&bar_w_full[0], Cfg::W_GRAN);
         bulk_load(sW, p.wpack, Cfg::W_GRAN, &bar_w_full[0]);
@@ -296,32 +584,23 @@ conv128_tc_kernel(ConvParams p) {
 
   fence_before_sync();
   __syncthreads();
-  if (warp == MMA_WARP) tmem_dealloc(tmem, 128);
+  if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 256);
 }
 
 // ---- stem: Conv2d(3 -> 128, KS, reflect) + bias, pixel-major output, GroupNorm partial sums ------
-// One CTA (128 threads) per 16x8 tile; thread = 4 output channels (weights in registers) x 32 pixels;
-// the 3-channel halo tile sits in shared memory and is read with warp-wide broadcasts.
+// CTAs of 128 threads walk 16x8 tiles of one image; thread = 4 output channels (weights in registers,
+// loaded once per CTA) x 32 pixels per tile; the 3-channel halo tile sits in shared memory and is
+// read with warp-wide broadcasts.
 template <int KS>
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ image, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                  const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
-                 float* __restrict__ part, int H, int W, int tiles_x) {
+                 float* __restrict__ part, int H, int W, int tiles_x, int tiles) {
   constexpr int HY = TH + KS - 1, WX = TW + KS - 1, NK = 3 * KS * KS;
   __shared__ __align__(16) float s_in[HY * WX][4];   // [halo pixel][channel (3) + pad]
   __shared__ float s_red[4][8][2];
   const int tid = threadIdx.x, q = tid & 31, slot = tid >> 5;
-  const int b = blockIdx.y, ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-  const int y0 = ty * TH, x0 = tx * TW;
-  for (int i = tid; i < HY * WX; i += 128) {
-    const int hy = i / WX, hx = i - hy * WX;
-    const int yy = reflect_clamp(y0 + hy - KS / 2, H), xx = reflect_clamp(x0 + hx - KS / 2, W);
-    const float* src = image + b * sb + yy * sy + xx * sx;
-    s_in[i][0] = src[0];
-    s_in[i][1] = src[sc];
-    s_in[i][2] = src[2 * sc];
-    s_in[i][3] = 0.f;
-  }
+  const int b = blockIdx.y;
   // weights (128, 3, KS, KS): wr[o][ (dy*KS+dx)*3 + ci ]
   float wr[4][NK];
 #pragma unroll
@@ -331,45 +610,59 @@ stem_conv_kernel(const float* __restrict__ image, int64_t sb, int64_t sc, int64_
 #pragma unroll
       for (int t = 0; t < KS * KS; ++t) wr[o][t * 3 + ci] = w[((4 * q + o) * 3 + ci) * KS * KS + t];
   const float4 bv = bias ? *reinterpret_cast<const float4*>(bias + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
-  float s = 0.f, ss = 0.f;
-#pragma unroll 2
-  for (int pi = slot; pi < TH * TW; pi += 4) {
-    const int py = pi >> 3, pxx = pi & 7;
-    float4 acc = bv;
-#pragma unroll
-    for (int dy = 0; dy < KS; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < KS; ++dx) {
-        const float4 in = *reinterpret_cast<const float4*>(&s_in[(py + dy) * WX + pxx + dx][0]);
-        const int t = (dy * KS + dx) * 3;
-        acc.x = fmaf(in.x, wr[0][t], fmaf(in.y, wr[0][t + 1], fmaf(in.z, wr[0][t + 2], acc.x)));
-        acc.y = fmaf(in.x, wr[1][t], fmaf(in.y, wr[1][t + 1], fmaf(in.z, wr[1][t + 2], acc.y)));
-        acc.z = fmaf(in.x, wr[2][t], fmaf(in.y, wr[2][t + 1], fmaf(in.z, wr[2][t + 2], acc.z)));
-        acc.w = fmaf(in.x, wr[3][t], fmaf(in.y, wr[3][t + 1], fmaf(in.z, wr[3][t + 2], acc.w)));
-      }
-    const int y = y0 + py, x = x0 + pxx;
-    if (y < H && x < W) {
-      stg_stream(out + ((int64_t(b) * H + y) * W + x) * CC + 4 * q, acc);
-      s += (acc.x + acc.y) + (acc.z + acc.w);
-      ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
-    }
-  }
-  if (part) {
-    // 4 adjacent lanes share a group (16 channels)
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-    if ((q & 3) == 0) {
-      s_red[slot][q >> 2][0] = s;
-      s_red[slot][q >> 2][1] = ss;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+    const int y0 = ty * TH, x0 = tx * TW;
+    __syncthreads();   // the previous tile's readers of s_in / s_red are done
+    for (int i = tid; i < HY * WX; i += 128) {
+      const int hy = i / WX, hx = i - hy * WX;
+      const int yy = reflect_clamp(y0 + hy - KS / 2, H), xx = reflect_clamp(x0 + hx - KS / 2, W);
+      const float* src = image + b * sb + yy * sy + xx * sx;
+      s_in[i][0] = src[0];
+      s_in[i][1] = src[sc];
+      s_in[i][2] = src[2 * sc];
+      s_in[i][3] = 0.f;
     }
     __syncthreads();
-    if (tid < 16) {
-      const int g = tid >> 1, which = tid & 1;
-      const float v = (s_red[0][g][which] + s_red[1][g][which]) + (s_red[2][g][which] + s_red[3][g][which]);
-      part[(int64_t(b) * gridDim.x + blockIdx.x) * 16 + tid] = v;
+    float s = 0.f, ss = 0.f;
+#pragma unroll 2
+    for (int pi = slot; pi < TH * TW; pi += 4) {
+      const int py = pi >> 3, pxx = pi & 7;
+      float4 acc = bv;
+#pragma unroll
+      for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx) {
+          const float4 in = *reinterpret_cast<const float4*>(&s_in[(py + dy) * WX + pxx + dx][0]);
+          const int t = (dy * KS + dx) * 3;
+          acc.x = fmaf(in.x, wr[0][t], fmaf(in.y, wr[0][t + 1], fmaf(in.z, wr[0][t + 2], acc.x)));
+          acc.y = fmaf(in.x, wr[1][t], fmaf(in.y, wr[1][t + 1], fmaf(in.z, wr[1][t + 2], acc.y)));
+          acc.z = fmaf(in.x, wr[2][t], fmaf(in.y, wr[2][t + 1], fmaf(in.z, wr[2][t + 2], acc.z)));
+          acc.w = fmaf(in.x, wr[3][t], fmaf(in.y, wr[3][t + 1], fmaf(in.z, wr[3][t + 2], acc.w)));
+        }
+      const int y = y0 + py, x = x0 + pxx;
+      if (y < H && x < W) {
+        stg_stream(out + ((int64_t(b) * H + y) * W + x) * CC + 4 * q, acc);
+        s += (acc.x + acc.y) + (acc.z + acc.w);
+        ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+      }
+    }
+    if (part) {
+      // 4 adjacent lanes share a group (16 channels)
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      if ((q & 3) == 0) {
+        s_red[slot][q >> 2][0] = s;
+        s_red[slot][q >> 2][1] = ss;
+      }
+      __syncthreads();
+      if (tid < 16) {
+        const int g = tid >> 1, which = tid & 1;
+        const float v = (s_red[0][g][which] + s_red[1][g][which]) + (s_red[2][g][which] + s_red[3][g][which]);
+        part[(int64_t(b) * tiles + tile) * 16 + tid] = v;
+      }
     }
   }
 }
@@ -424,6 +717,21 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __half* __restri
 // ------------------------------------------------------------------------------------ host side
 namespace {
 
+template <int KS>
+int launch_conv_ws(const ConvParams& p, cudaStream_t st) {
+  using Ws = WsConvCfg<KS>;
+  auto kern = conv128_ws_kernel<KS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws::SMEM);
+  if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t total = int64_t(p.B) * p.tiles_y * p.tiles_x;
+  const int grid = int(total < sms ? total : sms);
+  kern<<<grid, WS_THREADS, Ws::SMEM, st>>>(p);
+  return check_launch("enc_conv(ws)");
+}
+
 template <int KS, int PASSES>
 int launch_conv(const ConvParams& p, cudaStream_t st) {
   using Cfg = ConvCfg<KS, PASSES>;
@@ -446,7 +754,7 @@ int launch_enc_conv(const float* in, const float* coef, const void* wpack, const
                     int64_t out_pix_stride, int out_ch_off, float* part, int B, int H, int W, int KS,
                     int passes, cudaStream_t st) {
   NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_conv: kernel size %d (1 or 3)", KS);
-  NAF_REQUIRE(passes == 1 || passes == 3, NAF_ERR_UNSUPPORTED, "enc_conv: passes must be 1 or 3");
+  NAF_REQUIRE(passes == 1 || passes == 3 || passes == -1, NAF_ERR_UNSUPPORTED, "enc_conv: passes must be 1 or 3");
   NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_conv: reflect padding needs H, W >= 2");
   NAF_REQUIRE(aligned32(in) && aligned16(wpack) && aligned16(out) && aligned16(coef) &&
                   out_pix_stride % 4 == 0 && out_ch_off % 4 == 0 && out_pix_stride >= out_ch_off + CC,
@@ -467,8 +775,10 @@ int launch_enc_conv(const float* in, const float* coef, const void* wpack, const
   p.W = W;
   p.tiles_y = (H + TH - 1) / TH;
   p.tiles_x = (W + TW - 1) / TW;
-  if (KS == 1) return passes == 1 ? launch_conv<1, 1>(p, st) : launch_conv<1, 3>(p, st);
-  return passes == 1 ? launch_conv<3, 1>(p, st) : launch_conv<3, 3>(p, st);
+  // passes: 1 = pipelined kernel, 3 = split-fp16 kernel, -1 = 1 pass on the non-pipelined kernel
+  // (kept for A/B measurements)
+  if (KS == 1) return passes == 1 ? launch_conv_ws<1>(p, st) : passes == 3 ? launch_conv<1, 3>(p, st) : launch_conv<1, 1>(p, st);
+  return passes == 1 ? launch_conv_ws<3>(p, st) : passes == 3 ? launch_conv<3, 3>(p, st) : launch_conv<3, 1>(p, st);
 }
 
 int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
@@ -477,10 +787,15 @@ int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int6
   NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_stem: reflect padding needs H, W >= 2");
   NAF_REQUIRE(aligned16(out) && (!bias || aligned16(bias)), NAF_ERR_ALIGNMENT, "enc_stem: 16-byte alignment");
   NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "enc_stem: batch too large");
-  const int tiles_y = (H + TH - 1) / TH, tiles_x = (W + TW - 1) / TW;
-  const dim3 grid(unsigned(tiles_y * tiles_x), unsigned(B), 1u);
-  if (KS == 1) stem_conv_kernel<1><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x);
-  else stem_conv_kernel<3><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x);
+  const int tiles_y = (H + TH - 1) / TH, tiles_x = (W + TW - 1) / TW, tiles = tiles_y * tiles_x;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_img = (sms * 4 + B - 1) / B;   // ~4 CTAs of 128 threads per SM over the whole batch
+  if (per_img > tiles) per_img = tiles;
+  const dim3 grid(unsigned(per_img), unsigned(B), 1u);
+  if (KS == 1) stem_conv_kernel<1><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
+  else stem_conv_kernel<3><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
   return check_launch("enc_stem");
 }
 
