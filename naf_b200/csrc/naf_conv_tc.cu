@@ -94,6 +94,21 @@ __device__ __forceinline__ float silu(float t) {
   }
 }
 
+// packed fp32x2 helpers (FFMA2 on sm_100): two floats in one 64-bit register
+__device__ __forceinline__ uint64_t pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __device__ __forceinline__ void named_bar_workers() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 }  // namespace
@@ -332,24 +347,38 @@ conv128_tc_kernel(ConvParams p) {
 // ---- pipelined variant (1 pass): producer / MMA / epilogue warps work on different tiles ---------
 // One persistent CTA per SM.  A (the activated halo tile) and the TMEM accumulator are double
 // buffered, so at any time the 8 producer warps convert tile t+1 while the tensor core runs tile t
-// and the 8 epilogue warps drain tile t-1:
-//   warps 0-7   producers : halo tile HBM -> GN affine -> SiLU -> fp16 -> sA[t & 1]; L2 prefetch of
-//                           the tile after next
-//   warps 8-15  epilogue  : TMEM acc[t & 1] -> +bias -> statistics -> per-warp transpose -> stores
-//   warp 16     mma       : 9 (or 1) taps x 8 k-steps of tcgen05.mma per tile
-//   warp 17     loader    : weight ring, as above
+// and the 4 epilogue warps drain tile t-1:
+//   warps 0-7   producers : halo tile HBM -> registers (software-pipelined: the loads of the next
+//                           batch of pixels, or of the next tile, are in flight while the current
+//                           batch goes through GN affine -> SiLU -> fp16 -> sA[t & 1]); one bulk L2
+//                           prefetch per halo row for the tile after next
+//   warps 8-11  epilogue  : TMEM acc[t & 1] -> +bias -> statistics -> per-warp transpose -> stores
+//   warp 12     mma       : 9 (or 1) taps x 8 k-steps of tcgen05.mma per tile
+//   warp 13     loader    : weight ring, as above
 namespace {
-constexpr int WS_THREADS = 2 * NWORK + 64;
-constexpr int WS_MMA_WARP = 2 * NWORK / 32;
+constexpr int WS_NPROD = 256, WS_NEPI = 128;
+constexpr int WS_THREADS = WS_NPROD + WS_NEPI + 64;
+constexpr int WS_MMA_WARP = (WS_NPROD + WS_NEPI) / 32;
 
 template <int KS>
 struct WsConvCfg {
   using Base = ConvCfg<KS, 1>;
   static constexpr int A_BUF = (Base::A_PLANE + 127) / 128 * 128;
-  static constexpr int STAGE = NWORK * STAGE_SLOT;
+  static constexpr int STAGE = WS_NEPI * STAGE_SLOT;
   static constexpr int W_OFF = 2 * A_BUF;
   static constexpr int STAGE_OFF = W_OFF + Base::NSLOT * Base::W_GRAN;
   static constexpr int SMEM = STAGE_OFF + STAGE;
+  static constexpr int NIT = (Base::HP + 15) / 16;   // halo pixels per producer thread
+  static constexpr int BS = KS == 3 ? 3 : 4;         // pixels per register batch
+  static constexpr int NB = NIT / BS;                // batches per tile (even)
+  static_assert(NIT % BS == 0 && NB % 2 == 0, "batching");
+};
+
+struct TileCtx {
+  const float* img;   // image base + this thread's channel chunk
+  const float* org;   // halo origin of the tile (dereferenced only when interior)
+  int b, y0, x0;
+  bool interior, valid;
 };
 }  // namespace
 
@@ -359,12 +388,14 @@ conv128_ws_kernel(ConvParams p) {
   using Cfg = ConvCfg<KS, 1>;
   using Ws = WsConvCfg<KS>;
   constexpr int WX = Cfg::WX, HP = Cfg::HP, CS = Cfg::CS, NT = Cfg::NT;
+  constexpr int BS = Ws::BS, NB = Ws::NB;
   constexpr bool kResident = NT == 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_a_full[2], bar_a_free[2], bar_acc_full[2], bar_acc_free[2], bar_w_full[2], bar_w_free[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float s_bias[CC];
-  __shared__ float s_part[2][8][8];
+  __shared__ __align__(16) float s_bias[CC];
+  __shared__ float s_part[2][4][16];
+  __shared__ int s_goff[Ws::NIT * 16];
 
   uint8_t* sW = smem + Ws::W_OFF;
   uint8_t* sStage = smem + Ws::STAGE_OFF;
@@ -375,92 +406,150 @@ conv128_ws_kernel(ConvParams p) {
   if (warp == WS_MMA_WARP) tmem_alloc(&tmem_base_s, 256);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_a_full[s], NWORK);
+      mbar_init(&bar_a_full[s], WS_NPROD);
       mbar_init(&bar_a_free[s], 1);
       mbar_init(&bar_acc_full[s], 1);
-      mbar_init(&bar_acc_free[s], NWORK);
+      mbar_init(&bar_acc_free[s], WS_NEPI);
       mbar_init(&bar_w_full[s], 1);
       mbar_init(&bar_w_free[s], 1);
     }
     fence_mbar_init();
   }
   if (tid < CC) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+  // global element offset of halo pixel px relative to the tile's halo origin (same for every tile)
+  for (int px = tid; px < Ws::NIT * 16; px += WS_THREADS) {
+    const int q = px < HP ? px : HP - 1, hy = q / WX, hx = q - hy * WX;
+    s_goff[px] = (hy * p.W + hx) * CC;
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp < 8) {
+  if (warp < WS_NPROD / 32) {
     // ============================================================================== PRODUCERS
     const int chunk = tid & 15, px0 = tid >> 4;
-    float sc[8], sh[8];
+    auto ctx_of = [&](int tile) {
+      TileCtx c;
+      c.valid = tile < total;
+      c.b = 0; c.y0 = 0; c.x0 = 0; c.interior = false; c.img = p.in; c.org = p.in;
+      if (c.valid) {
+        c.b = tile / tiles_per_img;
+        const int rem = tile - c.b * tiles_per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        c.y0 = ty * TH;
+        c.x0 = tx * TW;
+        c.interior = c.y0 >= KS / 2 && c.y0 + TH + KS / 2 <= p.H && c.x0 >= KS / 2 && c.x0 + TW + KS / 2 <= p.W;
+        c.img = p.in + int64_t(c.b) * p.H * p.W * CC + chunk * 8;
+        c.org = c.img + (int64_t(c.y0 - KS / 2) * p.W + (c.x0 - KS / 2)) * CC;
+      }
+      return c;
+    };
+    auto load_batch = [&](const TileCtx& c, int j, float (&v)[BS][8]) {
+#pragma unroll
+      for (int kk = 0; kk < BS; ++kk) {
+        const int px = px0 + 16 * (j * BS + kk);
+        if (HP % 16 == 0 || px < HP) {
+          const float* src;
+          if (c.interior) {
+            src = c.org + s_goff[px];
+          } else {
+            const int hy = px / WX, hx = px - hy * WX;
+            src = c.img + (int64_t(reflect_clamp(c.y0 + hy - KS / 2, p.H)) * p.W +
+                           reflect_clamp(c.x0 + hx - KS / 2, p.W)) * CC;
+          }
+#if NAF_CONV_EXP & 2
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[kk][e] = float(px + e);
+          (void)src;
+#else
+          ldg_stream8(src, v[kk]);
+#endif
+        }
+      }
+    };
+    uint64_t sc2[4], sh2[4];   // GroupNorm {scale, shift} of this thread's 8 channels, as pairs
+    const uint64_t nl2e2 = pack2(-1.4426950408889634f, -1.4426950408889634f), zero2 = 0ull;
+    auto convert_batch = [&](int j, float (&v)[BS][8], uint8_t* sA) {
+#pragma unroll
+      for (int kk = 0; kk < BS; ++kk) {
+        const int k = j * BS + kk;
+        if (HP % 16 == 0 || px0 + 16 * k < HP) {
+          uint4 hi;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint64_t t2 = fma2(pack2(v[kk][2 * e], v[kk][2 * e + 1]), sc2[e], sh2[e]);   // GN affine
+            const uint64_t u2 = fma2(t2, nl2e2, zero2);                                       // -t log2(e)
+            float u0, u1, t0, t1, e0, e1, r0, r1;
+            unpack2(u2, u0, u1);
+            unpack2(t2, t0, t1);
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(u0));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(u1));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(1.f + e0));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.f + e1));
+            const __half2 h = __floats2half2_rn(t0 * r0, t1 * r1);   // silu(t) = t / (1 + 2^(-t log2 e))
+            hp[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(sA + k * 256) = hi;
+        }
+      }
+    };
+
+    float va[BS][8], vb[BS][8];
+    TileCtx cur = ctx_of(blockIdx.x);
+    if (cur.valid) load_batch(cur, 0, va);
     int b_cur = -1, it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int y0 = ty * TH, x0 = tx * TW;
-      if (b != b_cur) {   // GroupNorm scale/shift of this thread's 8 channels for image b
-        b_cur = b;
-        const float4* cp = reinterpret_cast<const float4*>(p.coef + b * CC + chunk * 8);
+      const TileCtx nxt = ctx_of(tile + int(gridDim.x));
+      if (cur.b != b_cur) {
+        b_cur = cur.b;
+        const float4* cp = reinterpret_cast<const float4*>(p.coef + cur.b * CC + chunk * 8);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 c = __ldg(cp + j);
-          sc[2 * j] = c.x;
-          sh[2 * j] = c.y;
-          sc[2 * j + 1] = c.z;
-          sh[2 * j + 1] = c.w;
+          const float4 c = __ldg(cp + j);   // {scale, shift} of channels 2j, 2j+1
+          sc2[j] = pack2(c.x, c.z);
+          sh2[j] = pack2(c.y, c.w);
         }
       }
-      {   // L2 prefetch of the tile after next (one 128-byte line per 4 chunks)
-        const int t2 = tile + 2 * gridDim.x;
-        if (t2 < total && (chunk & 3) == 0) {
+      if (tid < Cfg::HY) {   // L2 prefetch of the tile after next: one bulk prefetch per halo row
+        const int t2 = tile + 2 * int(gridDim.x);
+        if (t2 < total) {
           const int b2 = t2 / tiles_per_img, rem2 = t2 - b2 * tiles_per_img;
           const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
-          const float* img2 = p.in + int64_t(b2) * p.H * p.W * CC + chunk * 8;
-          for (int px = px0; px < HP; px += 16) {
-            const int hy = px / WX, hx = px - hy * WX;
-            const int sy = reflect_clamp(ty2 * TH + hy - KS / 2, p.H), sx = reflect_clamp(tx2 * TW + hx - KS / 2, p.W);
-            prefetch_l2(img2 + (int64_t(sy) * p.W + sx) * CC);
-          }
+          const int yy = reflect_clamp(ty2 * TH - KS / 2 + tid, p.H);
+          const int span = WX < p.W ? WX : p.W;
+          int xs = tx2 * TW - KS / 2;
+          xs = xs < 0 ? 0 : (xs > p.W - span ? p.W - span : xs);
+          bulk_prefetch_l2(p.in + ((int64_t(b2) * p.H + yy) * p.W + xs) * CC, uint32_t(span) * CC * 4);
         }
       }
       if (it >= 2) mbar_wait(&bar_a_free[buf], ((it >> 1) - 1) & 1);
-      uint8_t* sA = smem + buf * Ws::A_BUF;
-      const float* img = p.in + int64_t(b) * p.H * p.W * CC + chunk * 8;
-#pragma unroll 4
-      for (int px = px0; px < HP; px += 16) {
-        const int hy = px / WX, hx = px - hy * WX;
-        const int sy = reflect_clamp(y0 + hy - KS / 2, p.H), sx = reflect_clamp(x0 + hx - KS / 2, p.W);
-        float v[8];
-#if NAF_CONV_EXP & 2
+      uint8_t* sA = smem + buf * Ws::A_BUF + chunk * CS + px0 * 16;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = float(sy + sx + j);
-#else
-        ldg_stream8(img + (int64_t(sy) * p.W + sx) * CC, v);
-#endif
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = silu<true>(fmaf(v[j], sc[j], sh[j]));
-        const __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-        const __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
-        uint4 hi;
-        hi.x = *reinterpret_cast<const uint32_t*>(&h0);
-        hi.y = *reinterpret_cast<const uint32_t*>(&h1);
-        hi.z = *reinterpret_cast<const uint32_t*>(&h2);
-        hi.w = *reinterpret_cast<const uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(sA + chunk * CS + px * 16) = hi;
+      for (int j = 0; j < NB; j += 2) {
+        load_batch(cur, j + 1, vb);
+        convert_batch(j, va, sA);
+        if (j + 2 < NB) load_batch(cur, j + 2, va);
+        else if (nxt.valid) load_batch(nxt, 0, va);
+        convert_batch(j + 1, vb, sA);
       }
       fence_proxy_async_smem();
       mbar_arrive(&bar_a_full[buf]);
+      cur = nxt;
     }
-  } else if (warp < 16) {
+  } else if (warp < WS_MMA_WARP) {
     // =============================================================================== EPILOGUE
-    const int ew = warp - 8, et = tid - NWORK;
-    const int row = (ew & 3) * 32 + lane, hf = ew >> 2;
-    const uint32_t lane_off = uint32_t((ew & 3) * 32) << 16;
+    // warp ew owns TMEM lanes (pixels) [32 ew, 32 ew + 32); a thread drains its pixel's 128 channels
+    // in 4 rounds of 32 columns, each round transposed through the warp's private smem slab so that
+    // every store instruction writes four 128-byte runs (4 pixels x 32 channels).
+    const int ew = warp - WS_NPROD / 32, et = tid - WS_NPROD;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
     uint8_t* my_stage = sStage + et * STAGE_SLOT;
     const uint8_t* warp_stage = sStage + ew * 32 * STAGE_SLOT;
     const int sub = lane >> 3, piece = lane & 7;
+    const uint64_t one2 = pack2(1.f, 1.f);
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -468,36 +557,35 @@ conv128_ws_kernel(ConvParams p) {
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int y0 = ty * TH, x0 = tx * TW;
       const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
-      const int ybase = y0 + (ew & 3) * 4, xbase = x0 + sub;
-      float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off +
-                     hf * 64 + piece * 4;
+      const int ybase = y0 + ew * 4, xbase = x0 + sub;
+      float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off + piece * 4;
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      float st[8];
+      uint64_t st2[16];   // [group][sum | sumsq], each as an (even, odd) channel pair
 #pragma unroll
-      for (int j = 0; j < 8; ++j) st[j] = 0.f;
+      for (int j = 0; j < 16; ++j) st2[j] = 0ull;
 #pragma unroll
-      for (int rd = 0; rd < 2; ++rd) {
+      for (int rd = 0; rd < 4; ++rd) {
         uint32_t r[32];
-        tmem_ld32(tmem + lane_off + buf * CC + hf * 64 + rd * 32, r);
+        tmem_ld32(tmem + lane_off + buf * CC + rd * 32, r);
         wait_ld();
-        if (rd == 1) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
+        if (rd == 3) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
           fence_before_sync();
           mbar_arrive(&bar_acc_free[buf]);
         }
         __syncwarp();   // the previous round's read-back of the slab is complete
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const int c = hf * 64 + rd * 32 + j;
-          float4 o;
-          o.x = __uint_as_float(r[j]) + s_bias[c];
-          o.y = __uint_as_float(r[j + 1]) + s_bias[c + 1];
-          o.z = __uint_as_float(r[j + 2]) + s_bias[c + 2];
-          o.w = __uint_as_float(r[j + 3]) + s_bias[c + 3];
+          const float4 bv = *reinterpret_cast<const float4*>(&s_bias[rd * 32 + j]);
+          const uint64_t o01 = fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), one2, pack2(bv.x, bv.y));
+          const uint64_t o23 = fma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), one2, pack2(bv.z, bv.w));
           const int g = rd * 2 + (j >> 4);
-          st[g * 2] += (o.x + o.y) + (o.z + o.w);
-          st[g * 2 + 1] += (o.x * o.x + o.y * o.y) + (o.z * o.z + o.w * o.w);
-          *reinterpret_cast<float4*>(my_stage + j * 4) = o;
+          st2[g * 2] = fma2(o01, one2, st2[g * 2]);
+          st2[g * 2] = fma2(o23, one2, st2[g * 2]);
+          st2[g * 2 + 1] = fma2(o01, o01, st2[g * 2 + 1]);
+          st2[g * 2 + 1] = fma2(o23, o23, st2[g * 2 + 1]);
+          *reinterpret_cast<uint4*>(my_stage + j * 4) =
+              make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
         }
         __syncwarp();
 #pragma unroll
@@ -510,18 +598,16 @@ conv128_ws_kernel(ConvParams p) {
       }
       if (p.part) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float v = valid ? st[j] : 0.f;
+        for (int j = 0; j < 16; ++j) {
+          float v0, v1;
+          unpack2(st2[j], v0, v1);
+          float v = valid ? v0 + v1 : 0.f;
           v = warp_sum(v);
           if (lane == 0) s_part[buf][ew][j] = v;
         }
-        asm volatile("bar.sync 2, 256;" ::: "memory");
-        if (et < 16) {
-          const int g = et >> 1, which = et & 1, w0 = (g >> 2) * 4, gl = g & 3;
-          const float s = (s_part[buf][w0][gl * 2 + which] + s_part[buf][w0 + 1][gl * 2 + which]) +
-                          (s_part[buf][w0 + 2][gl * 2 + which] + s_part[buf][w0 + 3][gl * 2 + which]);
-          p.part[int64_t(tile) * 16 + et] = s;
-        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (et < 16)
+          p.part[int64_t(tile) * 16 + et] = (s_part[buf][0][et] + s_part[buf][1][et]) + (s_part[buf][2][et] + s_part[buf][3][et]);
       }
     }
   } else if (warp == WS_MMA_WARP) {

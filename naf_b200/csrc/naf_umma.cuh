@@ -206,6 +206,10 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
       "l"(gsrc), "r"(bytes), "r"(smem_u32(mbar))
       : "memory");
 }
+// L2 prefetch of a contiguous global range (16-byte aligned, size multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
