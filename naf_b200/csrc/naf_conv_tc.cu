@@ -366,7 +366,11 @@ struct WsConvCfg {
   static constexpr int A_BUF = (Base::A_PLANE + 127) / 128 * 128;
   static constexpr int STAGE = WS_NEPI * STAGE_SLOT;
   static constexpr int W_OFF = 2 * A_BUF;
-  static constexpr int STAGE_OFF = W_OFF + Base::NSLOT * Base::W_GRAN;
+#ifndef NAF_CONV_WSLOTS
+#define NAF_CONV_WSLOTS 3
+#endif
+  static constexpr int NSLOT = Base::NT == 1 ? 1 : NAF_CONV_WSLOTS;   // weight ring depth (taps in flight)
+  static constexpr int STAGE_OFF = W_OFF + NSLOT * Base::W_GRAN;
   static constexpr int SMEM = STAGE_OFF + STAGE;
   static constexpr int NIT = (Base::HP + 15) / 16;   // halo pixels per producer thread
   static constexpr int BS = KS == 3 ? 3 : 4;         // pixels per register batch
@@ -391,7 +395,7 @@ conv128_ws_kernel(ConvParams p) {
   constexpr int BS = Ws::BS, NB = Ws::NB;
   constexpr bool kResident = NT == 1;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_a_full[2], bar_a_free[2], bar_acc_full[2], bar_acc_free[2], bar_w_full[2], bar_w_free[2];
+  __shared__ uint64_t bar_a_full[2], bar_a_free[2], bar_acc_full[2], bar_acc_free[2], bar_w_full[4], bar_w_free[4];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[CC];
   __shared__ float s_part[2][4][16];
@@ -410,6 +414,8 @@ conv128_ws_kernel(ConvParams p) {
       mbar_init(&bar_a_free[s], 1);
       mbar_init(&bar_acc_full[s], 1);
       mbar_init(&bar_acc_free[s], WS_NEPI);
+    }
+    for (int s = 0; s < 4; ++s) {
       mbar_init(&bar_w_full[s], 1);
       mbar_init(&bar_w_free[s], 1);
     }
@@ -615,6 +621,8 @@ conv128_ws_kernel(ConvParams p) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, CC, false, false);
       const uint32_t w_base = smem_u32(sW);
+      constexpr int NS = Ws::NSLOT;
+      uint32_t slot = 0, wphase = 0;   // ring position of the next tap and its mbarrier phase
       uint32_t n = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -626,8 +634,7 @@ conv128_ws_kernel(ConvParams p) {
         const uint32_t tD = tmem + buf * CC;
 #pragma unroll 1
         for (int tap = 0; tap < NT; ++tap, ++n) {
-          const int slot = kResident ? 0 : int(n & 1);
-          if (!kResident) mbar_wait(&bar_w_full[slot], (n >> 1) & 1);
+          if (!kResident) mbar_wait(&bar_w_full[slot], wphase);
           else if (n == 0) mbar_wait(&bar_w_full[0], 0);
           const int dy = tap / KS, dx = tap - dy * KS;
           const uint32_t a0 = a_base + (dy * WX + dx) * 16;
@@ -638,7 +645,10 @@ conv128_ws_kernel(ConvParams p) {
             const uint64_t db = make_desc(b0 + kk * 2 * (CC * 16), CC * 16, 128);
             if (!(NAF_CONV_EXP & 4)) mma_f16_ss(tD, da, db, idesc, (tap | kk) != 0);
           }
-          if (!kResident) commit(&bar_w_free[slot]);
+          if (!kResident) {
+            commit(&bar_w_free[slot]);
+            if (++slot == NS) { slot = 0; wphase ^= 1; }
+          }
         }
         commit(&bar_a_free[buf]);
         commit(&bar_acc_full[buf]);
@@ -652,15 +662,17 @@ conv128_ws_kernel(ConvParams p) {
         mbar_expect_tx(&bar_w_full[0], Cfg::W_GRAN);
         bulk_load(sW, p.wpack, Cfg::W_GRAN, &bar_w_full[0]);
       } else {
-        uint32_t n = 0;
+        constexpr int NS = Ws::NSLOT;
+        uint32_t slot = 0, fphase = 1;   // fphase: parity of the PREVIOUS use's "free" completion
+        bool first_round = true;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
 #pragma unroll 1
-          for (int tap = 0; tap < NT; ++tap, ++n) {
-            const int slot = int(n & 1);
-            if (n >= 2) mbar_wait(&bar_w_free[slot], ((n >> 1) - 1) & 1);
+          for (int tap = 0; tap < NT; ++tap) {
+            if (!first_round) mbar_wait(&bar_w_free[slot], fphase);
             mbar_expect_tx(&bar_w_full[slot], Cfg::W_GRAN);
             bulk_load(sW + slot * Cfg::W_GRAN, p.wpack + size_t(tap) * 2 * W_PLANE, Cfg::W_GRAN,
                       &bar_w_full[slot]);
+            if (++slot == NS) { slot = 0; fphase ^= 1; first_round = false; }
           }
         }
       }
