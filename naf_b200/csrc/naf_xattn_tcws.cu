@@ -10,10 +10,11 @@
 //                          softmax on S (tcgen05.ld), P back to TMEM over S.
 //   warps 8-15  "back"  : drain O from TMEM, normalise, stage the output row slabs in shared
 //                          memory and hand them to the TMA engine (cp.async.bulk shared->global):
-//                          output stores cost no LSU wavefronts and never stall a warp.  Also
-//                          stages the NEXT item's K / V windows (double buffered).
+//                          output stores cost no LSU wavefronts and never stall a warp.
 //   warp 16     "mma"   : one thread issues every tcgen05.mma in the order
 //                          QK(0) QK(1) PV(0) QK(2) PV(1) ...  and commits to mbarriers.
+//   warps 17-18 "stage" : convert the NEXT item's K / V windows (fp32 -> fp16 hi/lo, UMMA layouts)
+//                          into the second window buffer.
 //
 // An "item" is (batch, cell, head, value-slab): wide value heads (dv = 256 with an 11x11 window)
 // are split into `vsplit` slabs of DV channels so that windows and accumulators fit; the slabs of
@@ -32,8 +33,14 @@ namespace {
 
 constexpr int DQ = 64;
 constexpr int KC = DQ / 8;
-constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 32;
+constexpr int NFRONT = 256, NBACK = 256, NSTAGE = 64, NTHREADS = NFRONT + NBACK + 32 + NSTAGE;
 constexpr int MMA_WARP = (NFRONT + NBACK) / 32;
+#ifndef NAF_WS_EPI
+#define NAF_WS_EPI 0     // output stores: 0 = one bulk copy (TMA engine) per thread and half row; 1 = per-warp transposed
+#endif                   // read-back + 128-byte-run st.global (measured 11 % slower at C2: 5.16 vs 4.63 ms)
+#ifndef NAF_WS_EXP
+#define NAF_WS_EXP 0     // profiling variants: 1 = no output stores, 2 = no q loads, 4 = no window staging after the first item
+#endif
 #ifndef NAF_WS_MEXCH
 #define NAF_WS_MEXCH 1   // row-max exchange between the two row halves: 1 = smem pad, 0 = re-read S from TMEM
 #endif
@@ -104,52 +111,69 @@ __device__ __forceinline__ ItemCoord decode_item(int item, const WsDivs& dv) {
 }
 
 // Stage the K and V windows of one item into a window buffer (fp32 -> fp16 hi/lo, UMMA
-// canonical layouts).  Executed by `nthreads` threads with linear id `t`.
+// canonical layouts).  Executed by `nthreads` threads with linear id `t`.  The global loads of U
+// elements are issued back to back before the first conversion, so their latencies overlap.
 template <int TP, int DV, int ROUNDS>
 __device__ __forceinline__ void stage_windows(uint8_t* win, const naf_xattn_params& p,
                                               const ItemCoord& it, int vchan0, int t, int nthreads) {
   using Cfg = WsCfg<TP, DV, ROUNDS>;
   constexpr int K = WsWindowOf<TP>::K, K2 = K * K;
+  constexpr int U = 4;
   uint8_t* sKhi = win;
   uint8_t* sKlo = sKhi + Cfg::kSmemK;
   uint8_t* sVhi = sKlo + Cfg::kSmemK;
   uint8_t* sVlo = sVhi + Cfg::kSmemV;
   const int wy0 = window_origin(it.ci, p.h, K);
   const int wx0 = window_origin(it.cj, p.w, K);
+  const float* kbase = p.k + (int64_t(it.b * p.h + wy0) * p.w + wx0) * p.D + it.head * DQ;
+  const float* vbase = p.v + (int64_t(it.b * p.h + wy0) * p.w + wx0) * p.C + vchan0;
   // K: canonical K-major [chunk c][tap n][16 B], zero rows for n >= K2
-#pragma unroll 2
-  for (int i = t; i < TP * KC; i += nthreads) {
-    const int n = i % TP, c = i / TP;
-    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-    if (n < K2) {
-      const int tt = n / K, u = n - tt * K;
-      const float* src = p.k + (int64_t(it.b * p.h + wy0 + tt) * p.w + wx0 + u) * p.D + it.head * DQ + c * 8;
-      float x[8];
-      ldg8(src, x);
-      ws_split8(x, hi, lo);
+  for (int i0 = t; i0 < TP * KC; i0 += U * nthreads) {
+    float x[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nthreads;
+      const int n = i % TP, c = i / TP;
+      const bool ok = i < TP * KC && n < K2;
+      const int tt = n / K, uu = n - tt * K;
+      ldg8(ok ? kbase + (int64_t(tt) * p.w + uu) * p.D + c * 8 : kbase, x[u]);
     }
-    *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
-    *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < TP * KC) {
+        const int n = i % TP, c = i / TP;
+        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+        if (n < K2) ws_split8(x[u], hi, lo);
+        *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
+        *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
+      }
+    }
   }
   // V: canonical MN-major [tap group][channel group][tap%8][16 B]
   constexpr int NG = DV / 8;
-#pragma unroll 4
-  for (int i = t; i < TP * NG; i += nthreads) {
-    const int kk = i & 7;
-    const int g = (i >> 3) % NG;
-    const int kg = (i >> 3) / NG;
-    const int k = kg * 8 + kk;
-    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-    if (k < K2) {
-      const int tt = k / K, u = k - tt * K;
-      const float* src = p.v + (int64_t(it.b * p.h + wy0 + tt) * p.w + wx0 + u) * p.C + vchan0 + g * 8;
-      float x[8];
-      ldg8(src, x);
-      ws_split8(x, hi, lo);
+  for (int i0 = t; i0 < TP * NG; i0 += U * nthreads) {
+    float x[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nthreads;
+      const int k = ((i >> 3) / NG) * 8 + (i & 7), g = (i >> 3) % NG;
+      const bool ok = i < TP * NG && k < K2;
+      const int tt = k / K, uu = k - tt * K;
+      ldg8(ok ? vbase + (int64_t(tt) * p.w + uu) * p.C + g * 8 : vbase, x[u]);
     }
-    const int off = (kg * NG + g) * 128 + kk * 16;
-    *reinterpret_cast<uint4*>(sVhi + off) = hi;
-    *reinterpret_cast<uint4*>(sVlo + off) = lo;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * nthreads;
+      if (i < TP * NG) {
+        const int kk = i & 7, g = (i >> 3) % NG, kg = (i >> 3) / NG;
+        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+        if (kg * 8 + kk < K2) ws_split8(x[u], hi, lo);
+        const int off = (kg * NG + g) * 128 + kk * 16;
+        *reinterpret_cast<uint4*>(sVhi + off) = hi;
+        *reinterpret_cast<uint4*>(sVlo + off) = lo;
+      }
+    }
   }
 }
 
@@ -161,7 +185,7 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
   using Cfg = WsCfg<TP, DV, ROUNDS>;
   constexpr int K2 = WsWindowOf<TP>::K * WsWindowOf<TP>::K;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_win_full[2], bar_o_full, bar_o_free;
+  __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_win_full[2], bar_win_free[2], bar_o_full, bar_o_free;
   __shared__ uint32_t tmem_base_s;
 
   uint8_t* win0 = smem;
@@ -183,7 +207,8 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
       mbar_init(&bar_q_full[s], NFRONT);
       mbar_init(&bar_s_full[s], 1);
       mbar_init(&bar_p_full[s], NFRONT);
-      mbar_init(&bar_win_full[s], NBACK);
+      mbar_init(&bar_win_full[s], NSTAGE);
+      mbar_init(&bar_win_free[s], 1);
     }
     mbar_init(&bar_o_full, 1);
     mbar_init(&bar_o_free, NBACK);
@@ -226,10 +251,16 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
       q_x = it.cj * rw + (pi - py * rw);
       const float* qp = p.q + int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
                         int64_t(fdiv(q_y, dv.rep_y)) * p.q_stride_y + int64_t(fdiv(q_x, dv.rep_x)) * p.q_stride_x;
+#if NAF_WS_EXP & 2
+#pragma unroll
+      for (int j = 0; j < P; ++j) { qa[j] = 0.01f * float(j + (pi & 7)); qb[j] = -0.02f * float(j); }
+      (void)qp;
+#else
       ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
       ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
       ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
       ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+#endif
     };
     // rotate + scale + split the prefetched q and write it to TMEM:
     // columns [0,32) hi, [32,64) lo; two channels per 32-bit column
@@ -383,7 +414,6 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
     const int bw = warp - 8;
     const int rowgrp = bw & 3, half = bw >> 2;
     const int row = rowgrp * 32 + lane;
-    const int bt = tid - NFRONT;
     const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
     constexpr int RC = Cfg::kRoundCols;   // output columns staged per round
     constexpr int HC = RC / 2;            // ... of which this thread owns a contiguous half
@@ -391,15 +421,6 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
     int g = 0;
     for (int it_seq = 0; it_seq < my_items; ++it_seq) {
       const ItemCoord it = item_of(it_seq);
-      // stage the NEXT item's windows into the other buffer (its last reader, item it_seq-1, has
-      // been fully drained by this group)
-      if (it_seq + 1 < my_items) {
-        uint8_t* nxt = ((it_seq + 1) & 1) ? win1 : win0;
-        const ItemCoord itn = item_of(it_seq + 1);
-        stage_windows<TP, DV, ROUNDS>(nxt, p, itn, vchan_of(itn), bt, NBACK);
-        fence_proxy_async_smem();
-        mbar_arrive(&bar_win_full[(it_seq + 1) & 1]);
-      }
       float* obase = p.out + int64_t(it.b) * p.Ho * p.Wo * p.C + vchan_of(it) + half * HC;
       for (int tile = 0; tile < ntiles; ++tile, ++g) {
         const int pi = tile * tile_rows + row;
@@ -408,10 +429,21 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
         const int y = it.ci * rh + py, x = it.cj * rw + (pi - py * rw);
         float* orow = obase + (int64_t(y) * p.Wo + x) * p.C;
         float inv_l = 0.f;
+#if NAF_WS_EPI
+        // lanes per contiguous run of the read-back (8 x 16 B = 128 B when the half row allows it)
+        constexpr int PW = (HC % 32 == 0) ? 8 : 4;
+        constexpr int RPI = 32 / PW, NCH = HC * 4 / (PW * 16);
+        const int rsub = lane / PW, piece = lane % PW;
+        const uint8_t* warp_stage = stage_out + (rowgrp * 32) * Cfg::kRowBytes + half * HC * 4;
+        // global address of this lane's output row (0 = no row), handed to the other lanes by shuffle
+        const uint64_t my_gp = valid ? reinterpret_cast<uint64_t>(orow) : 0ull;
+#endif
 #pragma unroll
         for (int rd = 0; rd < ROUNDS; ++rd) {
+#if !NAF_WS_EPI
           // the previous bulk store must have finished READING this thread's staging bytes
           bulk_wait_read<0>();
+#endif
           if (rd == 0) {
             mbar_wait(&bar_o_full, g & 1);
             fence_after_sync();
@@ -439,14 +471,49 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
                               __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
             }
           }
+#if NAF_WS_EPI
+          // the warp reads its 32 half rows back transposed: every store instruction writes RPI
+          // runs of PW*16 contiguous bytes (one run per pixel row)
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 32 / RPI; ++i) {
+            const int rr = i * RPI + rsub;
+            const uint32_t gp_lo = __shfl_sync(0xffffffffu, uint32_t(my_gp), rr);
+            const uint32_t gp_hi = __shfl_sync(0xffffffffu, uint32_t(my_gp >> 32), rr);
+            float* gp = reinterpret_cast<float*>((uint64_t(gp_hi) << 32) | gp_lo);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+              const float4 v = *reinterpret_cast<const float4*>(warp_stage + rr * Cfg::kRowBytes + (ch * PW + piece) * 16);
+              if (gp) stg_stream(gp + rd * RC + (ch * PW + piece) * 4, v);
+            }
+          }
+          __syncwarp();   // read-back done before the next round / tile overwrites the slab
+#else
           // this thread's slab -> TMA engine (it only reads bytes this thread wrote)
           fence_proxy_async_smem();
-          if (valid) bulk_store(orow + rd * RC, my_stage, HC * 4);
+          if (valid && !(NAF_WS_EXP & 1)) bulk_store(orow + rd * RC, my_stage, HC * 4);
           bulk_commit();
+#endif
         }
       }
     }
+#if !NAF_WS_EPI
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output writes performed
+#endif
+  } else if (warp > MMA_WARP) {
+    // ======================================================================== WINDOW STAGERS
+    // Two warps convert the K / V windows of item i+1 into the other window buffer while item i
+    // runs, so the pipeline never waits for a window (staged by the epilogue warps this cost 0.7 ms
+    // of 4.7 ms at C2).  A buffer is handed back by the MMA warp after the last PV that reads it.
+    const int st = tid - (NFRONT + NBACK + 32);
+    for (int it_seq = 1; it_seq < my_items; ++it_seq) {
+      const int b = it_seq & 1;
+      if (it_seq >= 2) mbar_wait(&bar_win_free[b], ((it_seq >> 1) - 1) & 1);
+      const ItemCoord itn = item_of(it_seq);
+      if (!(NAF_WS_EXP & 4)) stage_windows<TP, DV, ROUNDS>(b ? win1 : win0, p, itn, vchan_of(itn), st, NSTAGE);
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_win_full[b]);
+    }
   } else {
     // ======================================================================== MMA ISSUER
     if (lane == 0) {
@@ -485,6 +552,8 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
         mbar_wait(&bar_o_free, (g + 1) & 1);   // O drained by the epilogue of tile g-1
         fence_after_sync();
         const uint8_t* w = (pv_seq & 1) ? win1 : win0;
+        const int pv_item = pv_seq;
+        const bool last_of_item = pv_tile + 1 == ntiles;
         if (++pv_tile == ntiles) { pv_tile = 0; ++pv_seq; }
         const uint32_t tP = tmem + Cfg::kTmemS + s * TP;
         // O = Phi*Vhi + Plo*Vhi + Phi*Vlo
@@ -499,6 +568,8 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
           }
         }
         commit(&bar_o_full);
+        // every MMA that reads this item's windows has been issued: hand the buffer back to the stagers
+        if (last_of_item) commit(&bar_win_free[pv_item & 1]);
       };
       if (total_tiles > 0) issue_qk(0);
       for (int g = 0; g < total_tiles; ++g) {
