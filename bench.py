@@ -39,6 +39,8 @@ WORKLOADS = {
     "C3": (4, 1024, 518, 1036, 37, 11),
     "C4": (2, 768, 336, 1344, 24, 7),
     "C5": (4, 768, 512, 2048, 32, 7),
+    # the reference's own benchmark shape (test/test_utils.py:16-25): B=1, C=384, 448 -> 448, lr 28, K=9
+    "REF": (1, 384, 448, 448, 28, 9),
 }
 D_GUIDE = 256
 

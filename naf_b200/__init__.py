@@ -8,7 +8,7 @@ from . import _lib, ops, taps
 from .hub import ModelWrapper, naf
 from .layers import CrossAttention, RoPE, encoder
 from .model import NAF
-from .pipeline import HostPipeline
+from .pipeline import GraphedNAF, HostPipeline
 
-__all__ = ["NAF", "CrossAttention", "RoPE", "encoder", "naf", "ModelWrapper", "HostPipeline", "ops", "taps", "_lib"]
+__all__ = ["NAF", "CrossAttention", "RoPE", "encoder", "naf", "ModelWrapper", "HostPipeline", "GraphedNAF", "ops", "taps", "_lib"]
 __version__ = "0.1.0"

@@ -75,8 +75,9 @@ class ImageEncoder(nn.Module):
         Ho, Wo = int(output_size[0]), int(output_size[1])
         image = self._capped(image, Ho, Wo)
         Hs, Ws = image.shape[-2:]
-        if not (image.is_cuda and self.use_encoder and Ho % Hs == 0 and Wo % Ws == 0):
+        if not (image.is_cuda and self.use_encoder):
             return self.forward_encoder(image, (Ho, Wo)), (1, 1)
+        replicate = Ho % Hs == 0 and Wo % Ws == 0
         if (self.fast_encoder and self.tc_encoder and encoder_fast.tc_supported(self.encoder)
                 and encoder_fast.tc_supported(self.sem_encoder) and Hs >= 2 and Ws >= 2):
             # whole conv stack on our tcgen05 kernels; both branches write their 128-channel slab
@@ -85,7 +86,14 @@ class ImageEncoder(nn.Module):
             x = torch.empty((B, Hs, Ws, 2 * 128), device=image.device, dtype=torch.float32)
             encoder_fast.forward_tc(self.encoder, image, out=x, ch_off=0)
             encoder_fast.forward_tc(self.sem_encoder, image, out=x, ch_off=128)
-            return x.permute(0, 3, 1, 2), (Ho // Hs, Wo // Ws)
+            x = x.permute(0, 3, 1, 2)
+            if replicate:
+                return x, (Ho // Hs, Wo // Ws)
+            # true pooling (target below the encoder resolution, or a non-integer ratio): ATen's
+            # adaptive_avg_pool2d on the pixel-major map, exactly the reference's op (naf.py:34)
+            return F.adaptive_avg_pool2d(x, output_size=(Ho, Wo)), (1, 1)
+        if not replicate:
+            return self.forward_encoder(image, (Ho, Wo)), (1, 1)
         if (self.fast_encoder and image.dtype == torch.float32 and encoder_fast.supported(self.encoder)
                 and encoder_fast.supported(self.sem_encoder)):
             # our GroupNorm/SiLU/pad kernels between cuDNN convs, pixel-major end to end

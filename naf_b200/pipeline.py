@@ -85,3 +85,48 @@ class HostPipeline:
         main = torch.cuda.current_stream(self.device)
         main.wait_stream(self.s_in)
         main.wait_stream(self.s_out)
+
+
+class GraphedNAF:
+    """CUDA-graph replay of `NAF.forward` for latency-bound shapes (the reference's own benchmark
+    runs B=1: ~20 short kernels per forward, where launch overhead dominates).
+
+        fast = naf_b200.GraphedNAF(model)
+        out = fast(image, features, output_size)      # first call per shape: warm-up + capture
+
+    One graph per (shapes, dtypes, output_size, conv precision class).  Inputs are copied into the
+    graph's static buffers on every call; the returned tensor is the graph's static output buffer and
+    is overwritten by the next call with the same shapes -- clone it to keep it.
+    """
+
+    def __init__(self, model, warmup: int = 2):
+        self.model = model
+        self.warmup = int(warmup)
+        self._entries = {}
+
+    @torch.no_grad()
+    def __call__(self, image: torch.Tensor, features: torch.Tensor, output_size):
+        if not image.is_cuda or not features.is_cuda:
+            raise RuntimeError("GraphedNAF needs CUDA tensors (no CPU fallback)")
+        size = (int(output_size[0]), int(output_size[1]))
+        key = (tuple(image.shape), image.dtype, tuple(features.shape), features.dtype, size,
+               bool(torch.backends.cudnn.allow_tf32), image.device.index)
+        e = self._entries.get(key)
+        if e is None:
+            img_s, ft_s = image.clone(), features.clone()
+            side = torch.cuda.Stream(image.device)
+            side.wait_stream(torch.cuda.current_stream(image.device))
+            with torch.cuda.stream(side):      # warm-up off the capture: builds tables, weight images, pools
+                for _ in range(self.warmup):
+                    self.model(img_s, ft_s, size)
+            torch.cuda.current_stream(image.device).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out_s = self.model(img_s, ft_s, size)
+            e = (graph, img_s, ft_s, out_s)
+            self._entries[key] = e
+        graph, img_s, ft_s, out_s = e
+        img_s.copy_(image)
+        ft_s.copy_(features)
+        graph.replay()
+        return out_s

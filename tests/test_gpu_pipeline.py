@@ -45,3 +45,20 @@ def test_host_pipeline_matches_direct_calls():
     with torch.no_grad():
         w = reduce(m(img.to(dev), ft.to(dev), (32, 32))).cpu()
     assert torch.equal(res_h, w)
+
+
+def test_graphed_forward_matches_eager():
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(1)
+    m = naf_b200.NAF(kernel_size=7).eval().to(dev)
+    fast = naf_b200.GraphedNAF(m)
+    for shape in [((1, 3, 64, 64), (1, 32, 8, 8), (64, 64)), ((2, 3, 32, 48), (2, 16, 8, 8), (64, 96))]:
+        for i in range(3):
+            img = rnd(50 + i, *shape[0]).to(dev)
+            ft = rnd(60 + i, *shape[1]).to(dev)
+            got = fast(img, ft, shape[2]).clone()
+            with torch.no_grad():
+                want = m(img, ft, shape[2])
+            assert got.shape == want.shape and got.stride() == want.stride()
+            assert torch.equal(got, want)
+    assert len(fast._entries) == 2
