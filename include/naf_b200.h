@@ -13,7 +13,7 @@
  *   guidance  x / q : (B, Ho, Wo, D)   channel stride 1, pixel strides free (>= D, 16 B aligned)
  *   keys      k     : (B, h,  w,  D)   contiguous
  *   values    v     : (B, h,  w,  C)   contiguous
- *   output    out   : (B, Ho, Wo, C)   contiguous  (the reference also returns pixel-major
+ *   output    out   : (B, Ho, Wo, C)   contiguous, fp32 or bf16 (naf_xattn_params.out_dtype)  (the reference also returns pixel-major
  *                                       storage: src/layers/attentions.py:75 is a permuted view)
  *   scores          : (B, n, Ho, Wo, K*K) contiguous, tap order t_h*K + t_w
  */
@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NAF_ABI_VERSION 1
+#define NAF_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NAF_API __attribute__((visibility("default")))
@@ -125,7 +125,7 @@ typedef struct naf_xattn_params {
   const float* q;        /* (B,Ho,Wo,D) channel stride 1 */
   const float* k;        /* (B,h,w,D) contiguous */
   const float* v;        /* (B,h,w,C) contiguous */
-  float* out;            /* (B,Ho,Wo,C) contiguous */
+  void* out;             /* (B,Ho,Wo,C) contiguous; float, or bf16 when out_dtype == NAF_DTYPE_BF16 */
   float* scores;         /* NULL or (B,heads,Ho,Wo,K*K) */
   const int32_t* row_tap;/* NULL or (Ho,K) */
   const int32_t* col_tap;/* NULL or (Wo,K) */
@@ -138,7 +138,13 @@ typedef struct naf_xattn_params {
   int64_t q_stride_b, q_stride_y, q_stride_x; /* elements */
   int32_t algo;          /* NAF_ALGO_* ; AUTO picks the fastest kernel that supports the request */
   int32_t rep_y, rep_x;  /* q is a replicated source map (B,Ho/rep_y,Wo/rep_x,D); see kpool */
+  int32_t out_dtype;     /* NAF_DTYPE_F32 (0) or NAF_DTYPE_BF16 (1): element type of `out` only.  bf16 is what the
+                            reference returns under torch.autocast(bfloat16) (train.py:120, denoising.py:209);
+                            arithmetic stays fp32, the result is rounded to nearest-even on the final store.
+                            Served by the pipelined tensor-core kernel and the generic kernel. */
 } naf_xattn_params;
+
+enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1 };
 
 enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2, NAF_ALGO_CELL_TC = 3,
        NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline */ };

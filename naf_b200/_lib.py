@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NAF_B200_LIB") or os.path.join(_HERE, "csrc", "libnaf_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NAF_OK, NAF_ERR_BAD_SHAPE, NAF_ERR_UNSUPPORTED, NAF_ERR_WINDOW, NAF_ERR_ALIGNMENT, NAF_ERR_NULL, NAF_ERR_CUDA = range(7)
 ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS = range(5)
@@ -49,13 +49,15 @@ class XAttnParams(C.Structure):
         ("Ho", C.c_int32), ("Wo", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("K", C.c_int32),
         ("scale", C.c_float),
         ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
-        ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32),
+        ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32), ("out_dtype", C.c_int32),
     ]
 
     def __init__(self, *a, **kw):
         super().__init__(*a, **kw)
         self.rep_y = self.rep_x = 1
 
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
 
 #: every symbol include/naf_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {

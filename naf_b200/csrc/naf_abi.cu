@@ -62,6 +62,8 @@ static int validate_xattn(const naf_xattn_params& p) {
   NAF_REQUIRE(p.rep_y >= 1 && p.rep_x >= 1 && p.Ho % p.rep_y == 0 && p.Wo % p.rep_x == 0,
               NAF_ERR_BAD_SHAPE, "xattn: replication factors (%d,%d) must divide the target size",
               p.rep_y, p.rep_x);
+  NAF_REQUIRE(p.out_dtype == NAF_DTYPE_F32 || p.out_dtype == NAF_DTYPE_BF16, NAF_ERR_UNSUPPORTED,
+              "xattn: out_dtype %d (0 = f32, 1 = bf16)", p.out_dtype);
   return NAF_OK;
 }
 

@@ -5,6 +5,8 @@
 //
 // Reference semantics: src/layers/attentions.py:16-29 (QK -> *scale -> softmax -> AV),
 // :53-75 (dilation, layouts); tap order t_h*K + t_w (NATTEN).
+#include <cuda_bf16.h>
+
 #include "naf_common.cuh"
 
 namespace naf {
@@ -83,14 +85,15 @@ xattn_generic_kernel(naf_xattn_params p, int rh, int rw, int64_t total_items) {
     __syncwarp();
 
     // ---- aggregation: lane <-> value channel
-    float* op = p.out + ((int64_t(b) * p.Ho + y) * p.Wo + x) * p.C + head * dv;
+    const int64_t ooff = ((int64_t(b) * p.Ho + y) * p.Wo + x) * p.C + head * dv;
     for (int c0 = 0; c0 < dv; c0 += 32) {
       const int c = c0 + lane;
       float acc = 0.f;
       if (c < dv) {
         for (int tap = 0; tap < K2; ++tap)
           acc = fmaf(sc[tap], __ldg(p.v + int64_t(idx[tap]) * p.C + head * dv + c), acc);
-        op[c] = acc * inv;
+        if (p.out_dtype == NAF_DTYPE_BF16) static_cast<__nv_bfloat16*>(p.out)[ooff + c] = __float2bfloat16_rn(acc * inv);
+        else static_cast<float*>(p.out)[ooff + c] = acc * inv;
       }
     }
     __syncwarp();

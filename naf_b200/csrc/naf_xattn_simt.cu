@@ -86,7 +86,7 @@ xattn_cell_simt_kernel(naf_xattn_params p, int rh, int rw, int dv) {
   const int y0 = ci * rh, x0 = cj * rw;
   const float qscale = p.scale * 1.4426950408889634f;  // fold log2(e): softmax via exp2
   const float* qbase = p.q + int64_t(b) * p.q_stride_b + head * DQ;
-  float* obase = p.out + int64_t(b) * p.Ho * p.Wo * p.C + head * dv;
+  float* obase = static_cast<float*>(p.out) + int64_t(b) * p.Ho * p.Wo * p.C + head * dv;
 
   for (int ch = warp; ch < nchunks; ch += nwarps) {
     // ================= phase A: lane <-> pixel =================
@@ -232,6 +232,7 @@ static int cell_simt_warps(int K, int dq, int nj) {
 }
 
 bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why) {
+  if (p.out_dtype != NAF_DTYPE_F32) { *why = "fp32 output only"; return false; }
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }

@@ -149,7 +149,7 @@ xattn_cell_tc_kernel(naf_xattn_params p, int rh, int rw) {
   const float qscale = p.scale * 1.4426950408889634f;  // fold log2(e): softmax via exp2
   // this thread owns rotation pairs [16*half, 16*half+16): channels a = [16h,16h+16), b = a+32
   const float* qbase = p.q + int64_t(b) * p.q_stride_b + head * DQ + P * half;
-  float* obase = p.out + int64_t(b) * p.Ho * p.Wo * p.C + head * DV;
+  float* obase = static_cast<float*>(p.out) + int64_t(b) * p.Ho * p.Wo * p.C + head * DV;
 
   float qa[P], qb[P];   // raw (un-rotated) prefetched q of the NEXT tile, then rotated in place
   int64_t my_pix = -1;  // linear target pixel of this thread's row, or -1
@@ -414,6 +414,7 @@ int launch_tc_dv(const naf_xattn_params& p, cudaStream_t st) {
 }  // namespace
 
 bool xattn_cell_tc_supported(const naf_xattn_params& p, const char** why) {
+  if (p.out_dtype != NAF_DTYPE_F32) { *why = "fp32 output only"; return false; }
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }

@@ -22,6 +22,8 @@
 // Tiles are balanced (ceil(npix / ntiles) rows each) so a 28x28 cell is 7 x 112 rows.
 //
 // Reference semantics: src/layers/attentions.py:16-29,53-75; RoPE src/layers/rope.py:137-153.
+#include <cuda_bf16.h>
+
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
@@ -38,8 +40,14 @@ constexpr int MMA_WARP = (NFRONT + NBACK) / 32;
 #ifndef NAF_WS_EPI
 #define NAF_WS_EPI 0     // output stores: 0 = one bulk copy (TMA engine) per thread and half row; 1 = per-warp transposed
 #endif                   // read-back + 128-byte-run st.global (measured 11 % slower at C2: 5.16 vs 4.63 ms)
+#ifndef NAF_WS_DB
+#define NAF_WS_DB 0      // (measured slower: 5.25 vs 4.60 ms at C2) two-round epilogues alternate between two staging slabs per row (a bulk copy may still be
+#endif                   // reading slab A while the thread refills slab B)
+#ifndef NAF_WS_BLOCKED
+#define NAF_WS_BLOCKED 0 // item -> CTA map: 0 = round robin (the 4 heads of a cell run on neighbouring SMs at the same time), 1 = each CTA
+#endif                   // walks a contiguous range of items (measured slower: 5.0 vs 4.6 ms at C2)
 #ifndef NAF_WS_EXP
-#define NAF_WS_EXP 0     // profiling variants: 1 = no output stores, 2 = no q loads, 4 = no window staging after the first item
+#define NAF_WS_EXP 0     // profiling variants: 1 = no output stores, 2 = no q loads, 4 = no window staging after the first item, 8 = 16-byte stores
 #endif
 #ifndef NAF_WS_MEXCH
 #define NAF_WS_MEXCH 1   // row-max exchange between the two row halves: 1 = smem pad, 0 = re-read S from TMEM
@@ -55,7 +63,10 @@ struct WsCfg {
   static constexpr int kSmemV = TP * DV * 2;           // one of hi / lo
   static constexpr int kWin = 2 * kSmemK + 2 * kSmemV; // one window buffer (K hi|lo|V hi|lo)
   static constexpr int kRoundCols = DV / ROUNDS;       // output columns staged per round
-  static constexpr int kRowBytes = kRoundCols * 4 + 16;  // staged row + 16 B pad (bank spread)
+  // epilogues of exactly two rounds keep both rounds' slabs side by side in the row (double buffer)
+  static constexpr bool kDoubleStage = NAF_WS_DB && ROUNDS == 2;
+  static constexpr int kSlabs = kDoubleStage ? 2 : 1;
+  static constexpr int kRowBytes = kSlabs * kRoundCols * 4 + 16;  // staged row + 16 B pad (bank spread)
   static constexpr int kStage = 128 * kRowBytes;
   static constexpr int kSmemTotal = 2 * kWin + kStage;
   // Q: 64 columns per stage (32 hi + 32 lo); double buffered when TMEM allows, so that the next
@@ -196,9 +207,20 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
   const int npix = rh * rw;
   const int ntiles = (npix + 127) >> 7;
   const int tile_rows = (npix + ntiles - 1) / ntiles;   // balanced tiles, <= 128 rows
+#if NAF_WS_BLOCKED
+  // contiguous ranges: the first (n_items % grid) CTAs take one extra item
+  const int items_lo = n_items / int(gridDim.x), items_rem = n_items - items_lo * int(gridDim.x);
+  const int my_items = items_lo + (int(blockIdx.x) < items_rem ? 1 : 0);
+  const int my_first = int(blockIdx.x) * items_lo + min(int(blockIdx.x), items_rem);
+#else
   const int my_items = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+#endif
   const int dv_full = p.C / p.heads;                    // = vsplit * DV
+#if NAF_WS_BLOCKED
+  auto item_of = [&](int it_seq) { return decode_item(my_first + it_seq, dv); };
+#else
   auto item_of = [&](int it_seq) { return decode_item(blockIdx.x + it_seq * gridDim.x, dv); };
+#endif
   auto vchan_of = [&](const ItemCoord& it) { return it.head * dv_full + it.vh * DV; };
 
   if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, 512);
@@ -349,7 +371,7 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
       // The two halves of a row exchange their partial maxima through the 16-byte pad of the
       // row's staging slot (slot [tile parity][half]), and the same named barrier orders the S
       // reads of both halves before P overwrites the S columns.
-      float* mpad = reinterpret_cast<float*>(stage_out + row * Cfg::kRowBytes + Cfg::kRoundCols * 4) + s * 2;
+      float* mpad = reinterpret_cast<float*>(stage_out + row * Cfg::kRowBytes + Cfg::kSlabs * Cfg::kRoundCols * 4) + s * 2;
       mpad[half] = m;
       fence_before_sync();
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -417,17 +439,21 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
     const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
     constexpr int RC = Cfg::kRoundCols;   // output columns staged per round
     constexpr int HC = RC / 2;            // ... of which this thread owns a contiguous half
+    const bool bf16_out = p.out_dtype == NAF_DTYPE_BF16;
     uint8_t* my_stage = stage_out + row * Cfg::kRowBytes + half * HC * 4;
     int g = 0;
     for (int it_seq = 0; it_seq < my_items; ++it_seq) {
       const ItemCoord it = item_of(it_seq);
-      float* obase = p.out + int64_t(it.b) * p.Ho * p.Wo * p.C + vchan_of(it) + half * HC;
+      // element offset of this thread's half row slab inside the pixel; the output element is 4 bytes
+      // (fp32) or 2 bytes (bf16, rounded on this final store)
+      const int64_t obase = int64_t(it.b) * p.Ho * p.Wo * p.C + vchan_of(it) + half * HC;
       for (int tile = 0; tile < ntiles; ++tile, ++g) {
         const int pi = tile * tile_rows + row;
         const bool valid = row < tile_rows && pi < npix;
         const int py = fdiv(pi, dv.rw);
         const int y = it.ci * rh + py, x = it.cj * rw + (pi - py * rw);
-        float* orow = obase + (int64_t(y) * p.Wo + x) * p.C;
+        const int64_t oelem = obase + (int64_t(y) * p.Wo + x) * p.C;
+        float* orow = static_cast<float*>(p.out) + oelem;   // fp32 view (EPI=1 path and fp32 stores)
         float inv_l = 0.f;
 #if NAF_WS_EPI
         // lanes per contiguous run of the read-back (8 x 16 B = 128 B when the half row allows it)
@@ -441,8 +467,9 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
 #pragma unroll
         for (int rd = 0; rd < ROUNDS; ++rd) {
 #if !NAF_WS_EPI
-          // the previous bulk store must have finished READING this thread's staging bytes
-          bulk_wait_read<0>();
+          // the previous bulk store from THIS slab must have finished reading the thread's bytes
+          if constexpr (Cfg::kDoubleStage) bulk_wait_read<1>();
+          else bulk_wait_read<0>();
 #endif
           if (rd == 0) {
             mbar_wait(&bar_o_full, g & 1);
@@ -464,11 +491,27 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
               fence_before_sync();
               mbar_arrive(&bar_o_free);
             }
+            if (bf16_out) {
+              // 16 values -> 16 bf16 = two 16-byte chunks of the (half as long) staged slab
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              *reinterpret_cast<float4*>(my_stage + (c * 16 + j) * 4) =
-                  make_float4(__uint_as_float(r[c & 1][j]) * inv_l, __uint_as_float(r[c & 1][j + 1]) * inv_l,
-                              __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
+              for (int j = 0; j < 16; j += 8) {
+                uint4 pk;
+                uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[c & 1][j + 2 * e]) * inv_l,
+                                                                  __uint_as_float(r[c & 1][j + 2 * e + 1]) * inv_l);
+                  pw[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(my_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0) + (c * 16 + j) * 2) = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                *reinterpret_cast<float4*>(my_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0) + (c * 16 + j) * 4) =
+                    make_float4(__uint_as_float(r[c & 1][j]) * inv_l, __uint_as_float(r[c & 1][j + 1]) * inv_l,
+                                __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
+              }
             }
           }
 #if NAF_WS_EPI
@@ -483,7 +526,8 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
             float* gp = reinterpret_cast<float*>((uint64_t(gp_hi) << 32) | gp_lo);
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-              const float4 v = *reinterpret_cast<const float4*>(warp_stage + rr * Cfg::kRowBytes + (ch * PW + piece) * 16);
+              const float4 v = *reinterpret_cast<const float4*>(warp_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0) +
+                                                                rr * Cfg::kRowBytes + (ch * PW + piece) * 16);
               if (gp) stg_stream(gp + rd * RC + (ch * PW + piece) * 4, v);
             }
           }
@@ -491,7 +535,11 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
 #else
           // this thread's slab -> TMA engine (it only reads bytes this thread wrote)
           fence_proxy_async_smem();
-          if (valid && !(NAF_WS_EXP & 1)) bulk_store(orow + rd * RC, my_stage, HC * 4);
+          if (valid && !(NAF_WS_EXP & 1)) {
+            const uint8_t* src = my_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0);
+            if (bf16_out) bulk_store(static_cast<__nv_bfloat16*>(p.out) + oelem + rd * RC, src, HC * 2);
+            else bulk_store(orow + rd * RC, src, (NAF_WS_EXP & 8) ? 16 : HC * 4);
+          }
           bulk_commit();
 #endif
         }
@@ -646,6 +694,7 @@ struct WsPlan {
 
 template <int TP, int DV>
 constexpr int ws_rounds() {
+  if (NAF_WS_DB && DV % 64 == 0 && WsCfg<TP, DV, 2>::kFits) return 2;   // double-buffered staging
   if (WsCfg<TP, DV, 1>::kFits) return 1;
   if (DV % 64 == 0 && WsCfg<TP, DV, 2>::kFits) return 2;
   if (DV % 128 == 0 && WsCfg<TP, DV, 4>::kFits) return 4;
@@ -723,6 +772,7 @@ bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why) {
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }
   if (p.scores) { *why = "score output requested"; return false; }
+  if (NAF_WS_EPI && p.out_dtype != NAF_DTYPE_F32) { *why = "fp32 output only in this build"; return false; }
   if (dq != DQ) { *why = "head dim must be 64"; return false; }
   if (p.K < 3) { *why = "kernel_size must be 3, 5, 7, 9 or 11"; return false; }
   if (dv % 32) { *why = "value head dim must be a multiple of 32"; return false; }

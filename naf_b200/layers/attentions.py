@@ -10,9 +10,19 @@ high-resolution grid (:20,24,72), this operator hands the low-resolution K and V
 """
 from __future__ import annotations
 
+import torch
 from torch import nn
 
 from .. import _lib, ops
+
+
+def autocast_out_dtype(device_type: str = "cuda") -> torch.dtype:
+    """Output dtype the reference would produce here: bf16 inside `torch.autocast(bfloat16)` (its
+    NATTEN calls then run in bf16: train.py:120, denoising.py:209), fp32 otherwise.  fp16 autocast
+    is not mirrored (the kernels offer fp32 and bf16 stores)."""
+    if torch.is_autocast_enabled(device_type) and torch.get_autocast_dtype(device_type) == torch.bfloat16:
+        return torch.bfloat16
+    return torch.float32
 
 
 class CrossAttention(nn.Module):
@@ -32,10 +42,12 @@ class CrossAttention(nn.Module):
             return int(ks[0])
         return int(ks)
 
-    def forward(self, q, k, v, image=None, return_weights=False, rope_tables=None, rep=(1, 1), **kwargs):
+    def forward(self, q, k, v, image=None, return_weights=False, rope_tables=None, rep=(1, 1), out_dtype=None,
+                **kwargs):
         hq, wq = q.shape[-2] * int(rep[0]), q.shape[-1] * int(rep[1])
         hk, wk = k.shape[-2:]
         self.dilation = (hq // hk, wq // wk)
         res = ops.xattn(q, k, v, self.num_heads, self._square_kernel(), scale=self.scale,
-                        rope_tables=rope_tables, return_scores=return_weights, algo=self.algo, rep=rep)
+                        rope_tables=rope_tables, return_scores=return_weights, algo=self.algo, rep=rep,
+                        out_dtype=autocast_out_dtype() if out_dtype is None else out_dtype)
         return res

@@ -132,7 +132,7 @@ class NAF(nn.Module):
         self.upsampler = CrossAttention(dim=dim, num_heads=heads_attn,
                                         kernel_size=(kernel_size, kernel_size))
 
-    def upsample_from_guidance(self, x, features, return_weights=False, rep=(1, 1)):
+    def upsample_from_guidance(self, x, features, return_weights=False, rep=(1, 1), out_dtype=None):
         """The hot path proper: pooled un-rotated guidance x (B,D,Ho/ry,Wo/rx) + features
         (B,C,h,w) -> (B,C,Ho,Wo).  Two kernel launches (+ one tiny packing launch for V)."""
         rope = self.image_encoder.rope
@@ -155,14 +155,21 @@ class NAF(nn.Module):
             k, q = ops.rope_kpool(x, tables, rope.num_heads, pooled_hw=(h, w), want_q=not fused, rep=rep)
         if fused:
             return self.upsampler(x, k, features, return_weights=return_weights, rope_tables=tables,
-                                  rep=rep)
-        return self.upsampler(q, k, features, return_weights=return_weights)
+                                  rep=rep, out_dtype=out_dtype)
+        return self.upsampler(q, k, features, return_weights=return_weights, out_dtype=out_dtype)
 
-    def forward(self, image, features, output_size, return_weights=False, *args, **kwargs):
+    def forward(self, image, features, output_size, return_weights=False, *args, out_dtype=None, **kwargs):
+        """`out_dtype`: None = what the reference returns in this context (bf16 under bf16 autocast,
+        else fp32); torch.float32 / torch.bfloat16 to choose.  All arithmetic is fp32 either way."""
         if torch.is_grad_enabled() and (features.requires_grad or image.requires_grad or
                                         any(p.requires_grad for p in self.parameters())):
             if torch.is_grad_enabled() and self.training:
                 raise RuntimeError("naf_b200.NAF is forward-only: use torch.no_grad() and .eval()")
         with torch.no_grad():
             x, rep = self.image_encoder.guidance_source(image, output_size)
-            return self.upsample_from_guidance(x, features, return_weights=return_weights, rep=rep)
+            if out_dtype is None:
+                from ..layers.attentions import autocast_out_dtype
+                out_dtype = autocast_out_dtype()
+            with torch.autocast("cuda", enabled=False):
+                return self.upsample_from_guidance(x.float(), features, return_weights=return_weights, rep=rep,
+                                                   out_dtype=out_dtype)

@@ -214,6 +214,7 @@ def device_tap_tables(Ho, Wo, h, w, K, dev):
 
 
 def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo, rep=(1, 1)):
+    """naf_xattn_params for these tensors (out may be fp32 or bf16)."""
     B, D, Ho, Wo = q.shape
     Ho, Wo = Ho * int(rep[0]), Wo * int(rep[1])
     _, Cn, h, w = v.shape
@@ -227,17 +228,20 @@ def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo
     p.q_stride_b, _, p.q_stride_y, p.q_stride_x = q.stride()
     p.algo = int(algo)
     p.rep_y, p.rep_x = int(rep[0]), int(rep[1])
+    p.out_dtype = _lib.DTYPE_BF16 if out.dtype == torch.bfloat16 else _lib.DTYPE_F32
     return p
 
 
 def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_size: int,
           scale: Optional[float] = None, rope_tables=None, return_scores: bool = False,
-          algo: int = _lib.ALGO_AUTO, rep=(1, 1)):
+          algo: int = _lib.ALGO_AUTO, rep=(1, 1), out_dtype: torch.dtype = torch.float32):
     """Cross-scale neighbourhood attention.  q (B,D,Ho,Wo), k (B,D,h,w), v (B,C,h,w), all
     NCHW-shaped; returns out (B,C,Ho,Wo) as a permuted view of pixel-major storage (exactly what
     the reference returns, src/layers/attentions.py:75) and optionally the scaled pre-softmax
     scores (B,heads,Ho,Wo,K*K).
 
+    out_dtype: torch.float32, or torch.bfloat16 (what the reference returns under bf16 autocast;
+    the arithmetic stays fp32, only the final store is rounded).
     rope_tables: if given, q is the UN-rotated map and RoPE is applied inside the kernel.
     rep: q is a replicated source map (see rope_kpool); the target size is q's size times rep."""
     dev = _require_cuda(q, k, v)
@@ -264,7 +268,9 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_
         k = pack_nhwc(k).permute(0, 3, 1, 2)
     if not v.permute(0, 2, 3, 1).is_contiguous():
         v = pack_nhwc(v).permute(0, 3, 1, 2)
-    out = torch.empty((B, Ho, Wo, Cn), device=dev, dtype=torch.float32)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise NotImplementedError(f"xattn: out_dtype {out_dtype} (float32 or bfloat16)")
+    out = torch.empty((B, Ho, Wo, Cn), device=dev, dtype=out_dtype)
     scores = (torch.empty((B, heads, Ho, Wo, K * K), device=dev, dtype=torch.float32)
               if return_scores else None)
     p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo, rep)

@@ -286,3 +286,34 @@ def test_full_size_properties(cfg):
     want0 = win[:, :, origin][:, :, :, origin]                   # per cell
     got0 = out0.reshape(1, Cv, h, r, h, r)
     assert (got0 - want0[:, :, :, None, :, None]).abs().max().item() <= 1e-5
+
+
+# ------------------------------------------------------------------ bf16 output
+@pytest.mark.parametrize("case", [(1, 256, 4, 768, 196, 196, 7, 7, 7), (2, 256, 4, 128, 64, 96, 8, 12, 5),
+                                  (1, 256, 4, 1024, 154, 154, 11, 11, 11), (1, 64, 4, 16, 32, 32, 13, 13, 9)])
+def test_bf16_output_is_the_rounded_fp32_output(case):
+    """out_dtype=bfloat16 changes only the final store: bit-identical to rounding the fp32 result."""
+    B, D, n, C, Ho, Wo, h, w, K = case
+    q, k, v = rnd(1, B, D, Ho, Wo).to(dev()), rnd(2, B, D, h, w).to(dev()), rnd(3, B, C, h, w).to(dev())
+    for algo in available_algos(q.shape, v.shape, n, K):
+        if algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TC):
+            with pytest.raises(NotImplementedError):
+                ops.xattn(q, k, v, n, K, algo=algo, out_dtype=torch.bfloat16)
+            continue
+        o32 = ops.xattn(q, k, v, n, K, algo=algo)
+        o16 = ops.xattn(q, k, v, n, K, algo=algo, out_dtype=torch.bfloat16)
+        assert o16.dtype == torch.bfloat16 and o16.shape == o32.shape and o16.stride() == o32.stride()
+        assert torch.equal(o16, o32.to(torch.bfloat16)), _lib.ALGO_NAMES[algo]
+
+
+def test_module_follows_bf16_autocast_like_the_reference():
+    m = naf_b200.NAF(kernel_size=7).eval().to(dev())
+    img, ft = rnd(4, 1, 3, 64, 64).to(dev()), rnd(5, 1, 32, 8, 8).to(dev())
+    o32 = m(img, ft, (64, 64))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        o16 = m(img, ft.to(torch.bfloat16), (64, 64))
+    assert o32.dtype == torch.float32 and o16.dtype == torch.bfloat16
+    o32b = m(img, ft.to(torch.bfloat16).float(), (64, 64))   # same rounded features, fp32 out
+    # (a different kernel may serve the bf16 request: equal up to one bf16 rounding step)
+    assert ((o16.float() - o32b).abs() <= 2.0 ** -7 * o32b.abs() + 1e-6).all()
+    assert m(img, ft, (64, 64), out_dtype=torch.bfloat16).dtype == torch.bfloat16
