@@ -332,6 +332,7 @@ def main():
     peak, peak_src = measured_hbm_peak()
     achieved = algo_bytes / (xattn_ms / 1e3) / 1e9
     chosen = ops.select_algo((B, D_GUIDE, to, to), (B, C, lo, lo), 4, K) if args.algo == "auto" else args.algo
+    traffic = ncu_traffic(chosen, args.workload)
 
     line = {
         "metric": "upsampled Mpix/s", "value": round(value, 3), "unit": "Mpix/s", "n_gpus": world,
@@ -352,7 +353,11 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"xattn ({chosen})", "achieved": round(achieved, 1),
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": ncu_traffic(chosen, args.workload),
+                     "traffic": traffic,
+                     # the same launch rated on the DRAM bytes ncu measured for it (the guidance map is read
+                     # at the encoder resolution through replication factors: less than the algorithmic x)
+                     "achieved_on_traffic": (round(traffic / (xattn_ms / 1e3) / 1e9, 1) if traffic else None),
+                     "frac_on_traffic": (round(traffic / (xattn_ms / 1e3) / 1e9 / peak, 4) if traffic else None),
                      "kernel_ms": round(xattn_ms, 4), "algorithmic_bytes": int(algo_bytes),
                      "peak_source": peak_src},
         "clocks": clocks,

@@ -767,16 +767,19 @@ stem_conv_kernel(const float* __restrict__ image, int64_t sb, int64_t sc, int64_
 
 // ---- GroupNorm coefficients from the per-tile partial sums (deterministic order, double) --------
 // coef[b][c] = { rstd*gamma[c], beta[c] - mean*rstd*gamma[c] }   (biased variance, torch GroupNorm)
+// One CTA per (image, group): 256 threads stride over the tiles, then a fixed-order tree reduction.
 __global__ void __launch_bounds__(256)
 gn_coef_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
                const float* __restrict__ beta, float2* __restrict__ coef, int tiles, double count, float eps) {
-  __shared__ float s_mean[8], s_rstd[8];
-  const int b = blockIdx.x, g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ double s_s[8], s_ss[8];
+  __shared__ float s_mean, s_rstd;
+  const int b = blockIdx.x, g = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double ds = 0.0, dss = 0.0;
-  const float* base = part + int64_t(b) * tiles * 16 + g * 2;
-  for (int i = lane; i < tiles; i += 32) {
-    ds += double(base[int64_t(i) * 16]);
-    dss += double(base[int64_t(i) * 16 + 1]);
+  const float2* base = reinterpret_cast<const float2*>(part + int64_t(b) * tiles * 16 + g * 2);
+  for (int i = threadIdx.x; i < tiles; i += 256) {
+    const float2 v = __ldg(base + int64_t(i) * 8);
+    ds += double(v.x);
+    dss += double(v.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -784,17 +787,27 @@ gn_coef_kernel(const float* __restrict__ part, const float* __restrict__ gamma,
     dss += __shfl_xor_sync(0xffffffffu, dss, o);
   }
   if (lane == 0) {
-    const double mean = ds / count;
-    double var = dss / count - mean * mean;
-    var = var < 0.0 ? 0.0 : var;
-    s_mean[g] = float(mean);
-    s_rstd[g] = float(1.0 / sqrt(var + double(eps)));
+    s_s[warp] = ds;
+    s_ss[warp] = dss;
   }
   __syncthreads();
-  if (threadIdx.x < CC) {
-    const int c = threadIdx.x;
-    const float a = s_rstd[c >> 4] * gamma[c];
-    coef[b * CC + c] = make_float2(a, beta[c] - s_mean[c >> 4] * a);
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tss = 0.0;
+    for (int w = 0; w < 8; ++w) {
+      ts += s_s[w];
+      tss += s_ss[w];
+    }
+    const double mean = ts / count;
+    double var = tss / count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    s_mean = float(mean);
+    s_rstd = float(1.0 / sqrt(var + double(eps)));
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    const int c = g * 16 + threadIdx.x;
+    const float a = s_rstd * gamma[c];
+    coef[b * CC + c] = make_float2(a, beta[c] - s_mean * a);
   }
 }
 
@@ -901,8 +914,9 @@ int launch_enc_gn_coef(const float* part, const float* gamma, const float* beta,
                        int W, float eps, cudaStream_t st) {
   NAF_REQUIRE(aligned16(coef), NAF_ERR_ALIGNMENT, "enc_gn_coef: 16-byte alignment");
   const int tiles = ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
-  gn_coef_kernel<<<B, 256, 0, st>>>(part, gamma, beta, reinterpret_cast<float2*>(coef), tiles,
-                                    double(H) * W * 16.0, eps);
+  NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "enc_gn_coef: batch too large");
+  gn_coef_kernel<<<dim3(unsigned(B), 8u, 1u), 256, 0, st>>>(part, gamma, beta, reinterpret_cast<float2*>(coef), tiles,
+                                                          double(H) * W * 16.0, eps);
   return check_launch("enc_gn_coef");
 }
 

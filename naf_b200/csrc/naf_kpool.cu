@@ -80,11 +80,15 @@ rope_kpool_kernel(naf_kpool_params p, int lanes, int groups, int bins_h, int bin
   if (active) {
     const float* xb = p.x + int64_t(b) * p.x_stride_b;
     float* qb = p.q_out ? p.q_out + int64_t(b) * p.Ho * p.Wo * p.D : nullptr;
-#pragma unroll 2
+    // pixel (yy, xx) of this group walks the bin row-major with stride `groups`: advance the
+    // coordinates incrementally instead of dividing per pixel
+    int yy = ys + group / bw, xx = xs + group % bw;
+    const int step_y = groups / bw, step_x = groups % bw;
+    const bool no_rep = p.rep_y == 1 && p.rep_x == 1;
+#pragma unroll 4
     for (int pi = group; pi < npix; pi += groups) {
-      const int yy = ys + pi / bw;
-      const int xx = xs + pi % bw;
-      const float* px = xb + int64_t(yy / p.rep_y) * p.x_stride_y + int64_t(xx / p.rep_x) * p.x_stride_x;
+      const float* px = no_rep ? xb + int64_t(yy) * p.x_stride_y + int64_t(xx) * p.x_stride_x
+                               : xb + int64_t(yy / p.rep_y) * p.x_stride_y + int64_t(xx / p.rep_x) * p.x_stride_x;
       float a[VEC], bb[VEC];
       load_vec_stream<VEC>(a, px + ca);
       load_vec_stream<VEC>(bb, px + ca + half);
@@ -112,6 +116,12 @@ rope_kpool_kernel(naf_kpool_params p, int lanes, int groups, int bins_h, int bin
       for (int v = 0; v < VEC; ++v) {
         sa[v] += a[v];
         sb[v] += bb[v];
+      }
+      yy += step_y;
+      xx += step_x;
+      if (xx >= xe) {
+        xx -= bw;
+        ++yy;
       }
     }
   }
