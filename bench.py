@@ -204,6 +204,8 @@ def main():
     ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tc", "cell_tcws"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-d2h", default="sample", choices=["sample", "full"])
+    ap.add_argument("--graph", type=int, default=0,
+                    help="1: also time NAF.forward replayed as a CUDA graph (naf_b200.GraphedNAF) and run e2e over it; measured no gain at C2 (9.80 vs 9.54 ms): the step is not launch bound")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -266,7 +268,8 @@ def main():
         sink["out"] = model.upsample_from_guidance(x_holder["x"], feats, rep=x_holder["rep"])
 
     d2h_buf = {}
-    pipe = naf_b200.HostPipeline(model, depth=2)
+    graphed = naf_b200.GraphedNAF(model) if args.graph else None
+    pipe = naf_b200.HostPipeline(graphed if graphed is not None else model, depth=2)
 
     def e2e_reduce(out):
         return out if args.e2e_d2h == "full" else out[:, :, r // 2::r, r // 2::r]
@@ -315,6 +318,15 @@ def main():
         x_holder.clear()
 
         # ---- timed: end to end from pinned host buffers through the public API
+        graph_ms = None
+        if graphed is not None:
+            # the forward as a CUDA-graph replay (same kernels, no per-launch host work), inputs resident
+            def step_graph():
+                sink["out"] = graphed(image, feats, target)
+            for _ in range(3):
+                step_graph()
+            graph_ms = timed(step_graph, args.steps) / args.steps
+            sink.clear()
         for _ in range(2):
             step_e2e()
         pipe.drain()
@@ -348,8 +360,12 @@ def main():
                 "d2h": ("full output" if args.e2e_d2h == "full" else
                         "result sample: the upsampled features at every cell centre (B,C,h,w)"),
                 "api": "naf_b200.HostPipeline.step (pinned host in -> pinned host out; H2D/D2H on side "
-                       "streams overlap the neighbouring steps' kernels)",
+                       "streams overlap the neighbouring steps' kernels)" +
+                       (" over naf_b200.GraphedNAF (CUDA-graph replay of the forward)" if graphed is not None else ""),
                 "serial_ms": round(e2e_serial_ms, 4)},
+        "graph_replay": ({"value": round(mpix_step / (graph_ms / 1e3), 3), "unit": "Mpix/s", "ms": round(graph_ms, 4),
+                          "what": "NAF.forward replayed as one CUDA graph (naf_b200.GraphedNAF), inputs resident"}
+                         if graph_ms else None),
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": f"xattn ({chosen})", "achieved": round(achieved, 1),
                      "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

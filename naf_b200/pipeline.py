@@ -22,6 +22,7 @@ class HostPipeline:
     def __init__(self, model, depth: int = 2, device=None):
         self.model = model
         self.depth = int(depth)
+        # `model`: a NAF module, or any callable with its signature (e.g. GraphedNAF)
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != "cuda":
             raise RuntimeError("HostPipeline needs the model on a CUDA device (no CPU fallback)")
@@ -103,6 +104,9 @@ class GraphedNAF:
         self.model = model
         self.warmup = int(warmup)
         self._entries = {}
+
+    def parameters(self):
+        return self.model.parameters()
 
     @torch.no_grad()
     def __call__(self, image: torch.Tensor, features: torch.Tensor, output_size):
