@@ -637,11 +637,17 @@ conv128_ws_kernel(ConvParams p) {
           if (!kResident) mbar_wait(&bar_w_full[slot], wphase);
           else if (n == 0) mbar_wait(&bar_w_full[0], 0);
           const int dy = tap / KS, dx = tap - dy * KS;
+#if NAF_CONV_EXP & 32
+          const uint32_t a0 = a_base + 0 * (dy + dx);   // every tap reads the unshifted, 128-byte aligned tile
+          constexpr int SBO_A = 128;
+#else
           const uint32_t a0 = a_base + (dy * WX + dx) * 16;
+          constexpr int SBO_A = WX * 16;
+#endif
           const uint32_t b0 = w_base + slot * Cfg::W_GRAN;
 #pragma unroll
           for (int kk = 0; kk < CC / 16; ++kk) {
-            const uint64_t da = make_desc(a0 + kk * 2 * CS, CS, WX * 16);
+            const uint64_t da = make_desc(a0 + kk * 2 * CS, CS, SBO_A);
             const uint64_t db = make_desc(b0 + kk * 2 * (CC * 16), CC * 16, 128);
             if (!(NAF_CONV_EXP & 4)) mma_f16_ss(tD, da, db, idesc, (tap | kk) != 0);
           }
