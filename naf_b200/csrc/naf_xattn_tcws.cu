@@ -14,7 +14,8 @@
 //   warp 16     "mma"   : one thread issues every tcgen05.mma in the order
 //                          QK(0) QK(1) PV(0) QK(2) PV(1) ...  and commits to mbarriers.
 //   warps 17-18 "stage" : convert the NEXT item's K / V windows (fp32 -> fp16 hi/lo, UMMA layouts)
-//                          into the second window buffer.
+//                          into the second window buffer -- for long items / large windows; otherwise
+//                          the back group does it between two items and these warps idle.
 //
 // An "item" is (batch, cell, head, value-slab): wide value heads (dv = 256 with an 11x11 window)
 // are split into `vsplit` slabs of DV channels so that windows and accumulators fit; the slabs of
@@ -192,7 +193,7 @@ __device__ __forceinline__ void stage_windows(uint8_t* win, const naf_xattn_para
 
 template <int TP, int DV, int ROUNDS>
 __global__ void __launch_bounds__(NTHREADS, 1)
-xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vsplit, WsDivs dv) {
+xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vsplit, WsDivs dv, int use_stagers) {
   using Cfg = WsCfg<TP, DV, ROUNDS>;
   constexpr int K2 = WsWindowOf<TP>::K * WsWindowOf<TP>::K;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -229,7 +230,7 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
       mbar_init(&bar_q_full[s], NFRONT);
       mbar_init(&bar_s_full[s], 1);
       mbar_init(&bar_p_full[s], NFRONT);
-      mbar_init(&bar_win_full[s], NSTAGE);
+      mbar_init(&bar_win_full[s], use_stagers ? NSTAGE : NBACK);
       mbar_init(&bar_win_free[s], 1);
     }
     mbar_init(&bar_o_full, 1);
@@ -444,6 +445,14 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
     int g = 0;
     for (int it_seq = 0; it_seq < my_items; ++it_seq) {
       const ItemCoord it = item_of(it_seq);
+      // without stager warps (short items / small windows) this group converts the NEXT item's windows
+      // itself; the buffer's last reader, item it_seq-1, has been fully drained by this group
+      if (!use_stagers && it_seq + 1 < my_items) {
+        const ItemCoord itn = item_of(it_seq + 1);
+        stage_windows<TP, DV, ROUNDS>(((it_seq + 1) & 1) ? win1 : win0, p, itn, vchan_of(itn), tid - NFRONT, NBACK);
+        fence_proxy_async_smem();
+        mbar_arrive(&bar_win_full[(it_seq + 1) & 1]);
+      }
       // element offset of this thread's half row slab inside the pixel; the output element is 4 bytes
       // (fp32) or 2 bytes (bf16, rounded on this final store)
       const int64_t obase = int64_t(it.b) * p.Ho * p.Wo * p.C + vchan_of(it) + half * HC;
@@ -554,7 +563,7 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
     // runs, so the pipeline never waits for a window (staged by the epilogue warps this cost 0.7 ms
     // of 4.7 ms at C2).  A buffer is handed back by the MMA warp after the last PV that reads it.
     const int st = tid - (NFRONT + NBACK + 32);
-    for (int it_seq = 1; it_seq < my_items; ++it_seq) {
+    for (int it_seq = 1; use_stagers && it_seq < my_items; ++it_seq) {
       const int b = it_seq & 1;
       if (it_seq >= 2) mbar_wait(&bar_win_free[b], ((it_seq >> 1) - 1) & 1);
       const ItemCoord itn = item_of(it_seq);
@@ -681,7 +690,12 @@ int launch_ws(const naf_xattn_params& p, int vsplit, cudaStream_t st) {
     dv.rw = make_fastdiv(uint32_t(rw));
     dv.rep_y = make_fastdiv(uint32_t(p.rep_y));
     dv.rep_x = make_fastdiv(uint32_t(p.rep_x));
-    kern<<<grid, NTHREADS, Cfg::kSmemTotal, st>>>(p, rh, rw, int(items), vsplit, dv);
+    // Dedicated stager warps pay off when an item is long enough to hide a 64-thread conversion of the
+    // next windows (measured: C3 9.4 -> 8.7 ms, C5 14.6 -> 13.7 ms) and lose when items are short or the
+    // windows small (C2 4.62 -> 4.76 ms, C1 0.064 -> 0.070 ms): then the epilogue warps stage, as before.
+    const int ntiles = (rh * rw + 127) / 128;
+    const int use_stagers = ntiles >= 6 && (TP >= 96 || ntiles >= 12);
+    kern<<<grid, NTHREADS, Cfg::kSmemTotal, st>>>(p, rh, rw, int(items), vsplit, dv, use_stagers);
     return check_launch("xattn_cell_tcws");
   }
 }
