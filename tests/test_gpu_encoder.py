@@ -17,7 +17,7 @@ from naf_b200.layers import encoder
 
 pytestmark = pytest.mark.gpu
 
-TOL = {3: 2e-5, 1: 4e-3, -1: 4e-3}   # -1: the non-pipelined 1-pass kernel (kept for A/B timing)
+TOL = {3: 2e-5, 1: 4e-3, -1: 4e-3, -3: 4e-3}   # -1, -3: alternative 1-pass kernels kept for A/B timing
 
 
 def dev():
@@ -38,7 +38,7 @@ def tile_partials(y_nhwc):
     return torch.stack([t.sum(dim=(2, 4, 6)), (t * t).sum(dim=(2, 4, 6))], dim=-1).view(B, ty * tx, 8, 2)
 
 
-SHAPES = [(1, 16, 8), (2, 37, 29), (1, 48, 40), (1, 2, 2), (3, 20, 100)]
+SHAPES = [(1, 16, 8), (2, 37, 29), (1, 48, 40), (1, 2, 2), (3, 20, 100), (1, 70, 17), (2, 64, 64)]
 
 
 @pytest.mark.parametrize("ks", [1, 3])
@@ -62,7 +62,7 @@ def test_stem_conv_and_partials(ks, shape):
     assert (part.cpu().double().view(B, tiles, 8, 2) - wp).abs().max().item() <= 1e-5 * max(1.0, wp.abs().max().item())
 
 
-@pytest.mark.parametrize("passes", [3, 1, -1])
+@pytest.mark.parametrize("passes", [3, 1, -1, -3])
 @pytest.mark.parametrize("ks", [1, 3])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_gn_silu_conv_kernel(ks, passes, shape):
@@ -103,11 +103,13 @@ def test_gn_silu_conv_kernel(ks, passes, shape):
     scale = want.abs().max().item()
     err = (got[..., 128:] - want).abs().max().item()
     assert err <= TOL[passes] * scale, (ks, passes, shape, err, scale)
-    wp = tile_partials(got[..., 128:].float())
-    assert (part_out.cpu().double().view(B, tiles, 8, 2) - wp).abs().max().item() <= 1e-5 * max(1.0, wp.abs().max().item())
+    # partial sums: kernels tile differently (16x8 or 32x8), what is pinned is the per-(image, group) total
+    wp = tile_partials(got[..., 128:].float()).sum(dim=1)
+    gp = part_out.cpu().double().view(B, tiles, 8, 2).sum(dim=1)
+    assert (gp - wp).abs().max().item() <= 1e-5 * max(1.0, wp.abs().max().item())
 
 
-@pytest.mark.parametrize("passes", [3, 1, -1])
+@pytest.mark.parametrize("passes", [3, 1, -1, -3])
 @pytest.mark.parametrize("ks", [1, 3])
 def test_whole_branch_matches_torch_modules(ks, passes):
     torch.manual_seed(3)
