@@ -387,7 +387,11 @@ conv128_tc_kernel(ConvParams p) {
 //   warp 12     mma       : 9 (or 1) taps x 8 k-steps of tcgen05.mma per tile
 //   warp 13     loader    : weight ring, as above
 namespace {
-constexpr int WS_NPROD = 256, WS_NEPI = 128;
+#ifndef NAF_CONV_NPROD
+#define NAF_CONV_NPROD 256
+#endif
+constexpr int WS_NPROD = NAF_CONV_NPROD, WS_NEPI = 128;   // producer threads: 256 or 384
+constexpr int WS_PXS = WS_NPROD / 16;                      // halo pixels converted concurrently
 constexpr int WS_THREADS = WS_NPROD + WS_NEPI + 64;
 constexpr int WS_MMA_WARP = (WS_NPROD + WS_NEPI) / 32;
 
@@ -403,9 +407,9 @@ struct WsConvCfg {
   static constexpr int NSLOT = Base::NT == 1 ? 1 : NAF_CONV_WSLOTS;   // weight ring depth (taps in flight)
   static constexpr int STAGE_OFF = W_OFF + NSLOT * Base::W_GRAN;
   static constexpr int SMEM = STAGE_OFF + STAGE;
-  static constexpr int NIT = (Base::HP + 15) / 16;   // halo pixels per producer thread
-  static constexpr int BS = KS == 3 ? 3 : 4;         // pixels per register batch
-  static constexpr int NB = NIT / BS;                // batches per tile (even)
+  static constexpr int NIT = (Base::HP + WS_PXS - 1) / WS_PXS;   // halo pixels per producer thread
+  static constexpr int BS = NIT / 2 > 4 ? NIT / 4 : NIT / 2;     // pixels per register batch
+  static constexpr int NB = NIT / BS;                            // batches per tile (even)
   static_assert(NIT % BS == 0 && NB % 2 == 0, "batching");
 };
 
@@ -430,7 +434,7 @@ conv128_ws_kernel(ConvParams p) {
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float s_bias[CC];
   __shared__ float s_part[2][4][16];
-  __shared__ int s_goff[Ws::NIT * 16];
+  __shared__ int s_goff[Ws::NIT * WS_PXS];
 
   uint8_t* sW = smem + Ws::W_OFF;
   uint8_t* sStage = smem + Ws::STAGE_OFF;
@@ -454,7 +458,7 @@ conv128_ws_kernel(ConvParams p) {
   }
   if (tid < CC) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
   // global element offset of halo pixel px relative to the tile's halo origin (same for every tile)
-  for (int px = tid; px < Ws::NIT * 16; px += WS_THREADS) {
+  for (int px = tid; px < Ws::NIT * WS_PXS; px += WS_THREADS) {
     const int q = px < HP ? px : HP - 1, hy = q / WX, hx = q - hy * WX;
     s_goff[px] = (hy * p.W + hx) * CC;
   }
@@ -484,8 +488,8 @@ conv128_ws_kernel(ConvParams p) {
     auto load_batch = [&](const TileCtx& c, int j, float (&v)[BS][8]) {
 #pragma unroll
       for (int kk = 0; kk < BS; ++kk) {
-        const int px = px0 + 16 * (j * BS + kk);
-        if (HP % 16 == 0 || px < HP) {
+        const int px = px0 + WS_PXS * (j * BS + kk);
+        if (HP % WS_PXS == 0 || px < HP) {
           const float* src;
           if (c.interior) {
             src = c.org + s_goff[px];
@@ -509,7 +513,7 @@ conv128_ws_kernel(ConvParams p) {
 #pragma unroll
       for (int kk = 0; kk < BS; ++kk) {
         const int k = j * BS + kk;
-        if (HP % 16 == 0 || px0 + 16 * k < HP) {
+        if (HP % WS_PXS == 0 || px0 + WS_PXS * k < HP) {
           uint4 hi;
           uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
 #pragma unroll
@@ -517,7 +521,7 @@ conv128_ws_kernel(ConvParams p) {
             const uint64_t t2 = fma2(pack2(v[kk][2 * e], v[kk][2 * e + 1]), sc2[e], sh2[e]);   // GN affine
             hp[e] = silu2_f16(t2);
           }
-          *reinterpret_cast<uint4*>(sA + k * 256) = hi;
+          *reinterpret_cast<uint4*>(sA + k * (WS_PXS * 16)) = hi;
         }
       }
     };
@@ -712,6 +716,7 @@ conv128_ws_kernel(ConvParams p) {
   if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 256);
 }
 
+#if NAF_CONV_NPROD == 256   // the operand-swapped variant is written for 256 producer threads
 // ---- 3x3, 1 pass, operands swapped: D[cout][pixel] = W[cout][cin] . Act[pixel][cin]^T, N = 256 pixels ----
 // Experiment kept as an alternative (passes = -3): a 128x128x16 MMA reads 8 KB of operands in 64 math
 // cycles and conv128_ws_kernel<3> refills 288 KB of weights per 128-pixel tile, so shared-memory
@@ -1072,6 +1077,8 @@ conv128_t_kernel(ConvParams p, int tiles16_x) {
   if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 512);
 }
 
+#endif
+
 // ---- stem: Conv2d(3 -> 128, KS, reflect) + bias, pixel-major output, GroupNorm partial sums ------
 // CTAs of 128 threads walk 16x8 tiles of one image; thread = 4 output channels (weights in registers,
 // loaded once per CTA) x 32 pixels per tile; the 3-channel halo tile sits in shared memory and is
@@ -1231,6 +1238,10 @@ int launch_conv_ws(const ConvParams& p, cudaStream_t st) {
 }
 
 int launch_conv_t(ConvParams p, cudaStream_t st) {
+#if NAF_CONV_NPROD != 256
+  (void)p; (void)st;
+  return fail(NAF_ERR_UNSUPPORTED, "enc_conv: the operand-swapped kernel is not part of this build");
+#else
   cudaError_t e = cudaFuncSetAttribute(conv128_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
   int dev = 0, sms = 148;
@@ -1243,6 +1254,7 @@ int launch_conv_t(ConvParams p, cudaStream_t st) {
   const int grid = int(total < sms ? total : sms);
   conv128_t_kernel<<<grid, WS_THREADS, T_SMEM, st>>>(p, tiles16_x);
   return check_launch("enc_conv(t)");
+#endif
 }
 
 template <int KS, int PASSES>
