@@ -35,16 +35,18 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def command(verbose: bool = False) -> list[str]:
-    cmd = [nvcc_path(), "-std=c++17", "-O3", "-lineinfo",
-           "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "-shared",
-           "-I", os.path.join(ROOT, "include"), "-I", HERE, "-DNAF_BUILDING_LIB", "-DNAF_WITH_TC",
-           "-o", LIB]
+def _flags(verbose: bool = False) -> list[str]:
+    flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+             "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden",
+             "-I", os.path.join(ROOT, "include"), "-I", HERE, "-DNAF_BUILDING_LIB", "-DNAF_WITH_TC"]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(HERE, s) for s in SOURCES]
-    return cmd
+        flags += ["-Xptxas", "-v"]
+    return flags
+
+
+def command(verbose: bool = False) -> list[str]:
+    """The equivalent single nvcc invocation (what build() does, file by file in parallel)."""
+    return [nvcc_path()] + _flags(verbose) + ["-shared", "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -53,11 +55,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
                 return LIB
-    res = subprocess.run(command(verbose), capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    from concurrent.futures import ThreadPoolExecutor
+
+    objdir = os.path.join(HERE, "_obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = nvcc_path()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc] + _flags(verbose) + ["-c", os.path.join(HERE, src), "-o", obj],
+                             capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = False
+    for src, _, res in results:
+        if verbose or res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+        failed |= res.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libnaf_b200.so")
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] +
+                         [obj for _, obj, _ in results], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libnaf_b200.so")
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB
