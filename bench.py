@@ -70,7 +70,7 @@ class ClockSampler(threading.Thread):
     BAD = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown"}
     NOTE = {0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x1: "gpu_idle", 0x2: "app_clocks"}
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -115,8 +115,8 @@ class ClockSampler(threading.Thread):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+        return {"sm_mhz": s[len(s) // 2], "sm_min_mhz": s[0], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
 
 
 # ------------------------------------------------------------------------------ CPU baseline
