@@ -210,6 +210,12 @@ NAF_API int naf_gn_silu_apply_f32(const float* y, const float* bias, const float
 NAF_API int naf_enc_stem_f32(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
                              int64_t stride_w, const float* weight, const float* bias, float* out,
                              float* part, int B, int H, int W, int KS, void* stream);
+/* The same stem as one 128x128x{16,32} tensor-core GEMM per 16x8 pixel tile (im2col rows built in shared
+ * memory, operands rounded to fp16: the TF32 precision class, see naf_enc_conv_f32 passes = 1).  HBM bound
+ * instead of FMA bound; identical arguments and partial-sum layout. */
+NAF_API int naf_enc_stem_tc_f32(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
+                                int64_t stride_w, const float* weight, const float* bias, float* out,
+                                float* part, int B, int H, int W, int KS, void* stream);
 NAF_API int naf_enc_gn_coef_f32(const float* part, const float* gamma, const float* beta, float* coef,
                                 int B, int H, int W, float eps, void* stream);
 NAF_API int naf_enc_conv_pack_f32(const float* weight, void* packed, int KS, void* stream);

@@ -77,6 +77,8 @@ EXPORTS = {
                                         C.c_int, C.c_float, C.c_int, _fp]),
     "naf_enc_stem_f32": (C.c_int, [_fp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp,
                                    C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "naf_enc_stem_tc_f32": (C.c_int, [_fp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp,
+                                      C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "naf_enc_gn_coef_f32": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_float, _fp]),
     "naf_enc_conv_pack_f32": (C.c_int, [_fp, _fp, C.c_int, _fp]),
     "naf_enc_conv_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, C.c_int, C.c_int,

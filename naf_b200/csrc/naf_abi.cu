@@ -209,6 +209,19 @@ int naf_enc_stem_f32(const float* image, int64_t stride_b, int64_t stride_c, int
                          KS, static_cast<cudaStream_t>(stream));
 }
 
+int naf_enc_stem_tc_f32(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
+                        int64_t stride_w, const float* weight, const float* bias, float* out, float* part,
+                        int B, int H, int W, int KS, void* stream) {
+  NAF_REQUIRE(image && weight && out, NAF_ERR_NULL, "enc_stem_tc: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_stem_tc: sizes must be positive");
+#ifndef NAF_WITH_TC
+  return fail(NAF_ERR_UNSUPPORTED, "enc_stem_tc: library built without the tensor-core path");
+#else
+  return launch_enc_stem_tc(image, stride_b, stride_c, stride_h, stride_w, weight, bias, out, part, B, H, W,
+                            KS, static_cast<cudaStream_t>(stream));
+#endif
+}
+
 int naf_enc_gn_coef_f32(const float* part, const float* gamma, const float* beta, float* coef, int B,
                         int H, int W, float eps, void* stream) {
   NAF_REQUIRE(part && gamma && beta && coef, NAF_ERR_NULL, "enc_gn_coef: NULL pointer");

@@ -132,6 +132,8 @@ int launch_enc_conv(const float* in, const float* coef, const void* wpack, const
                     int passes, cudaStream_t st);
 int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
                     const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st);
+int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
+                       const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st);
 int launch_enc_gn_coef(const float* part, const float* gamma, const float* beta, float* coef, int B, int H,
                        int W, float eps, cudaStream_t st);
 int launch_enc_conv_pack(const float* w, void* packed, int KS, cudaStream_t st);

@@ -375,6 +375,68 @@ conv128_tc_kernel(ConvParams p) {
   if (warp == MMA_WARP) tmem_dealloc(tmem, 128);
 }
 
+// Epilogue of one 16x8 tile for the pipelined kernels (4 warps, warp ew owns TMEM lanes = pixels
+// [32 ew, 32 ew + 32)): accumulator -> +bias -> GroupNorm partial sums -> per-warp transpose slab ->
+// stores of four 128-byte runs per instruction.  `tmem_acc` = accumulator base + this warp's lane offset.
+__device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem_acc, uint64_t* bar_acc_free, int b,
+                                              int y0, int x0, int tile, int ew, int lane, int et, uint8_t* my_stage,
+                                              const uint8_t* warp_stage, const float* s_bias, float (*s_part)[16]) {
+  const int row = ew * 32 + lane;
+  const int sub = lane >> 3, piece = lane & 7;
+  const uint64_t one2 = pack2(1.f, 1.f);
+  const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
+  const int ybase = y0 + ew * 4, xbase = x0 + sub;
+  float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off + piece * 4;
+  uint64_t st2[16];   // [group][sum | sumsq], each as an (even, odd) channel pair
+#pragma unroll
+  for (int j = 0; j < 16; ++j) st2[j] = 0ull;
+#pragma unroll
+  for (int rd = 0; rd < 4; ++rd) {
+    uint32_t r[32];
+    tmem_ld32(tmem_acc + rd * 32, r);
+    wait_ld();
+    if (rd == 3) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
+      fence_before_sync();
+      mbar_arrive(bar_acc_free);
+    }
+    __syncwarp();   // the previous round's read-back of the slab is complete
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      const float4 bv = *reinterpret_cast<const float4*>(&s_bias[rd * 32 + j]);
+      const uint64_t o01 = fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), one2, pack2(bv.x, bv.y));
+      const uint64_t o23 = fma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), one2, pack2(bv.z, bv.w));
+      const int g = rd * 2 + (j >> 4);
+      st2[g * 2] = fma2(o01, one2, st2[g * 2]);
+      st2[g * 2] = fma2(o23, one2, st2[g * 2]);
+      st2[g * 2 + 1] = fma2(o01, o01, st2[g * 2 + 1]);
+      st2[g * 2 + 1] = fma2(o23, o23, st2[g * 2 + 1]);
+      *reinterpret_cast<uint4*>(my_stage + j * 4) =
+          make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 o = *reinterpret_cast<const float4*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 16);
+      const int yy = ybase + (i >> 1), xx = xbase + (i & 1) * 4;
+      if (yy < p.H && xx < p.W && !(NAF_CONV_EXP & 1))
+        stg_stream(obase + (int64_t(i >> 1) * p.W + (i & 1) * 4) * p.out_pix_stride + rd * 32, o);
+    }
+  }
+  if (p.part) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float v0, v1;
+      unpack2(st2[j], v0, v1);
+      float v = valid ? v0 + v1 : 0.f;
+      v = warp_sum(v);
+      if (lane == 0) s_part[ew][j] = v;
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (et < 16)
+      p.part[int64_t(tile) * 16 + et] = (s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et]);
+  }
+}
+
 // ---- pipelined variant (1 pass): producer / MMA / epilogue warps work on different tiles ---------
 // One persistent CTA per SM.  A (the activated halo tile) and the TMEM accumulator are double
 // buffered, so at any time the 8 producer warps convert tile t+1 while the tensor core runs tile t
@@ -575,71 +637,19 @@ conv128_ws_kernel(ConvParams p) {
     // in 4 rounds of 32 columns, each round transposed through the warp's private smem slab so that
     // every store instruction writes four 128-byte runs (4 pixels x 32 channels).
     const int ew = warp - WS_NPROD / 32, et = tid - WS_NPROD;
-    const int row = ew * 32 + lane;
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
     uint8_t* my_stage = sStage + et * STAGE_SLOT;
     const uint8_t* warp_stage = sStage + ew * 32 * STAGE_SLOT;
-    const int sub = lane >> 3, piece = lane & 7;
-    const uint64_t one2 = pack2(1.f, 1.f);
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int y0 = ty * TH, x0 = tx * TW;
-      const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
-      const int ybase = y0 + ew * 4, xbase = x0 + sub;
-      float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off + piece * 4;
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      uint64_t st2[16];   // [group][sum | sumsq], each as an (even, odd) channel pair
-#pragma unroll
-      for (int j = 0; j < 16; ++j) st2[j] = 0ull;
-#pragma unroll
-      for (int rd = 0; rd < 4; ++rd) {
-        uint32_t r[32];
-        tmem_ld32(tmem + lane_off + buf * CC + rd * 32, r);
-        wait_ld();
-        if (rd == 3) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
-          fence_before_sync();
-          mbar_arrive(&bar_acc_free[buf]);
-        }
-        __syncwarp();   // the previous round's read-back of the slab is complete
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 bv = *reinterpret_cast<const float4*>(&s_bias[rd * 32 + j]);
-          const uint64_t o01 = fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), one2, pack2(bv.x, bv.y));
-          const uint64_t o23 = fma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), one2, pack2(bv.z, bv.w));
-          const int g = rd * 2 + (j >> 4);
-          st2[g * 2] = fma2(o01, one2, st2[g * 2]);
-          st2[g * 2] = fma2(o23, one2, st2[g * 2]);
-          st2[g * 2 + 1] = fma2(o01, o01, st2[g * 2 + 1]);
-          st2[g * 2 + 1] = fma2(o23, o23, st2[g * 2 + 1]);
-          *reinterpret_cast<uint4*>(my_stage + j * 4) =
-              make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 o = *reinterpret_cast<const float4*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 16);
-          const int yy = ybase + (i >> 1), xx = xbase + (i & 1) * 4;
-          if (yy < p.H && xx < p.W && !(NAF_CONV_EXP & 1))
-            stg_stream(obase + (int64_t(i >> 1) * p.W + (i & 1) * 4) * p.out_pix_stride + rd * 32, o);
-        }
-      }
-      if (p.part) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v0, v1;
-          unpack2(st2[j], v0, v1);
-          float v = valid ? v0 + v1 : 0.f;
-          v = warp_sum(v);
-          if (lane == 0) s_part[buf][ew][j] = v;
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (et < 16)
-          p.part[int64_t(tile) * 16 + et] = (s_part[buf][0][et] + s_part[buf][1][et]) + (s_part[buf][2][et] + s_part[buf][3][et]);
-      }
+      ws_drain_tile(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, y0, x0, tile, ew, lane, et, my_stage,
+                    warp_stage, s_bias, s_part[buf]);
     }
   } else if (warp == WS_MMA_WARP) {
     // ============================================================================= MMA ISSUER
@@ -1079,6 +1089,155 @@ conv128_t_kernel(ConvParams p, int tiles16_x) {
 
 #endif
 
+// ---- stem on the tensor core (1 pass): Conv2d(3 -> 128, KS, reflect) as a 128 x 128 x {16, 32} GEMM ----
+// The SIMT stem below is FMA bound (0.40 ms for the 3x3 stem at C2, 3x the time its 822 MB of output
+// needs).  Here the producers build the im2col row of every pixel directly in the K-major operand layout
+// (K index = tap*3 + channel, 27 of 32 used; 3 of 16 for the 1x1 stem), the weights sit in shared memory
+// for the whole kernel, and the epilogue is the one of the pipelined conv kernel (bias, GroupNorm
+// partial sums, transpose slab, 128-byte-run stores).  Operands are rounded to fp16 (the TF32 class);
+// the strict fp32 class keeps the SIMT kernel.
+template <int KS>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+stem_tc_kernel(ConvParams p, const float* __restrict__ image, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
+               const float* __restrict__ w) {
+  constexpr int NK = 3 * KS * KS;              // 27 or 3
+  constexpr int KDIM = NK > 16 ? 32 : 16;      // MMA K, zero padded
+  constexpr int NCH = KDIM / 8;                // 16-byte chunks per row
+  constexpr int A_BUF = NCH * 128 * 16;        // one operand tile
+  constexpr int STEM_W_OFF = 2 * A_BUF, STEM_STAGE_OFF = STEM_W_OFF + NCH * CC * 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_a_full[2], bar_a_free[2], bar_acc_full[2], bar_acc_free[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float s_bias[CC];
+  __shared__ float s_part[2][4][16];
+
+  uint8_t* sW = smem + STEM_W_OFF;
+  uint8_t* sStage = smem + STEM_STAGE_OFF;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tiles_per_img = p.tiles_y * p.tiles_x;
+  const int total = p.B * tiles_per_img;
+
+  if (warp == WS_MMA_WARP) tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_a_full[s], WS_NPROD);
+      mbar_init(&bar_a_free[s], 1);
+      mbar_init(&bar_acc_full[s], 1);
+      mbar_init(&bar_acc_free[s], WS_NEPI);
+    }
+    fence_mbar_init();
+  }
+  if (tid < CC) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+  // weights (128, 3, KS, KS) fp32 -> K-major fp16 [chunk][n][8], k = tap*3 + ci, zero padded
+  for (int i = tid; i < CC * KDIM; i += WS_THREADS) {
+    const int n = i / KDIM, k = i - n * KDIM;
+    float v = 0.f;
+    if (k < NK) {
+      const int tap = k / 3, ci = k - tap * 3;
+      v = w[(n * 3 + ci) * KS * KS + tap];
+    }
+    reinterpret_cast<__half*>(sW)[((k >> 3) * CC + n) * 8 + (k & 7)] = __float2half_rn(v);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp < WS_NPROD / 32) {
+    // ============================================================================== PRODUCERS
+    // thread = (pixel pp of the tile, half kh of the K range): 16 K values = two 16-byte chunks
+    const int pp = tid & 127, kh = tid >> 7;
+    const int py = pp >> 3, px = pp & 7;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int y = ty * TH + py, x = tx * TW + px;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = 0.f;
+      if (kh * 16 < NK) {
+        const float* img = image + int64_t(b) * sb;
+        int64_t roff[KS], coff[KS];
+#pragma unroll
+        for (int d = 0; d < KS; ++d) {
+          roff[d] = int64_t(reflect_clamp(y + d - KS / 2, p.H)) * sy;
+          coff[d] = int64_t(reflect_clamp(x + d - KS / 2, p.W)) * sx;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          // k = kh*16 + i; both halves are compiled, the runtime kh selects
+          const int k0 = i, k1 = 16 + i;
+          if (kh == 0 && k0 < NK) v[i] = __ldg(img + (k0 % 3) * sc + roff[(k0 / 3) / KS] + coff[(k0 / 3) % KS]);
+          if (kh == 1 && k1 < NK) v[i] = __ldg(img + (k1 % 3) * sc + roff[(k1 / 3) / KS] + coff[(k1 / 3) % KS]);
+        }
+      }
+      if (it >= 2) mbar_wait(&bar_a_free[buf], ((it >> 1) - 1) & 1);
+      if (kh * 2 < NCH) {
+        uint8_t* sA = smem + buf * A_BUF + (kh * 2) * (128 * 16) + pp * 16;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 hv;
+          uint32_t* hp = reinterpret_cast<uint32_t*>(&hv);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __half2 h = __floats2half2_rn(v[c * 8 + 2 * e], v[c * 8 + 2 * e + 1]);
+            hp[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(sA + c * (128 * 16)) = hv;
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bar_a_full[buf]);
+    }
+  } else if (warp < WS_MMA_WARP) {
+    // =============================================================================== EPILOGUE
+    const int ew = warp - WS_NPROD / 32, et = tid - WS_NPROD;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    uint8_t* my_stage = sStage + et * STAGE_SLOT;
+    const uint8_t* warp_stage = sStage + ew * 32 * STAGE_SLOT;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
+      fence_after_sync();
+      ws_drain_tile(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, ty * TH, tx * TW, tile, ew, lane, et, my_stage,
+                    warp_stage, s_bias, s_part[buf]);
+    }
+  } else if (warp == WS_MMA_WARP) {
+    // ============================================================================= MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, CC, false, false);
+      const uint32_t w_base = smem_u32(sW);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&bar_a_full[buf], (it >> 1) & 1);
+        if (it >= 2) mbar_wait(&bar_acc_free[buf], ((it >> 1) - 1) & 1);
+        fence_after_sync();
+        const uint32_t a_base = smem_u32(smem + buf * A_BUF);
+#pragma unroll
+        for (int kk = 0; kk < KDIM / 16; ++kk) {
+          const uint64_t da = make_desc(a_base + kk * 2 * (128 * 16), 128 * 16, 128);
+          const uint64_t db = make_desc(w_base + kk * 2 * (CC * 16), CC * 16, 128);
+          mma_f16_ss(tmem + buf * CC, da, db, idesc, kk != 0);
+        }
+        commit(&bar_a_free[buf]);
+        commit(&bar_acc_full[buf]);
+      }
+    }
+    __syncwarp();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 256);
+}
+
 // ---- stem: Conv2d(3 -> 128, KS, reflect) + bias, pixel-major output, GroupNorm partial sums ------
 // CTAs of 128 threads walk 16x8 tiles of one image; thread = 4 output channels (weights in registers,
 // loaded once per CTA) x 32 pixels per tile; the 3-channel halo tile sits in shared memory and is
@@ -1324,6 +1483,45 @@ int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int6
   if (KS == 1) stem_conv_kernel<1><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
   else stem_conv_kernel<3><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
   return check_launch("enc_stem");
+}
+
+int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
+                       const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st) {
+  NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_stem_tc: kernel size %d (1 or 3)", KS);
+  NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_stem_tc: reflect padding needs H, W >= 2");
+  NAF_REQUIRE(aligned16(out) && (!bias || aligned16(bias)), NAF_ERR_ALIGNMENT, "enc_stem_tc: 16-byte alignment");
+  ConvParams p;
+  p.in = nullptr;
+  p.coef = nullptr;
+  p.wpack = nullptr;
+  p.bias = bias;
+  p.out = out;
+  p.part = part;
+  p.out_pix_stride = CC;
+  p.out_ch_off = 0;
+  p.B = B;
+  p.H = H;
+  p.W = W;
+  p.tiles_y = (H + TH - 1) / TH;
+  p.tiles_x = (W + TW - 1) / TW;
+  NAF_REQUIRE(int64_t(B) * p.tiles_y * p.tiles_x < (int64_t(1) << 27), NAF_ERR_UNSUPPORTED, "enc_stem_tc: too many tiles");
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t total = int64_t(B) * p.tiles_y * p.tiles_x;
+  const int grid = int(total < sms ? total : sms);
+  const int nch = KS == 3 ? 4 : 2;
+  const int smem = 2 * nch * 128 * 16 + nch * CC * 16 + WS_NEPI * STAGE_SLOT;
+  cudaError_t e;
+  if (KS == 3) {
+    e = cudaFuncSetAttribute(stem_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) stem_tc_kernel<3><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
+  } else {
+    e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) stem_tc_kernel<1><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
+  }
+  if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_stem_tc: smem opt-in failed: %s", cudaGetErrorString(e));
+  return check_launch("enc_stem_tc");
 }
 
 int launch_enc_gn_coef(const float* part, const float* gamma, const float* beta, float* coef, int B, int H,

@@ -41,9 +41,12 @@ def tile_partials(y_nhwc):
 SHAPES = [(1, 16, 8), (2, 37, 29), (1, 48, 40), (1, 2, 2), (3, 20, 100), (1, 70, 17), (2, 64, 64)]
 
 
+@pytest.mark.parametrize("tc", [False, True], ids=["simt", "tensor-core"])
 @pytest.mark.parametrize("ks", [1, 3])
 @pytest.mark.parametrize("shape", SHAPES)
-def test_stem_conv_and_partials(ks, shape):
+def test_stem_conv_and_partials(ks, shape, tc):
+    """Stem conv: exact-fp32 SIMT kernel (1e-5) and the tensor-core GEMM variant (fp16-rounded operands,
+    the TF32 class: 4e-3 of max |value|); both emit the GroupNorm partial sums of what they stored."""
     B, H, W = shape
     conv = torch.nn.Conv2d(3, 128, ks, padding=ks // 2, padding_mode="reflect")
     img = rnd(1, B, 3, H, W)
@@ -54,11 +57,13 @@ def test_stem_conv_and_partials(ks, shape):
     tiles = -(-H // 16) * -(-W // 8)
     part = torch.full((B, tiles, 16), float("nan"), device=dev())
     sb, sc, sy, sx = x.stride()
-    rc = _lib.load().naf_enc_stem_f32(ops._ptr(x), sb, sc, sy, sx, ops._ptr(conv.weight), ops._ptr(conv.bias),
-                                      ops._ptr(out), ops._ptr(part), B, H, W, ks, ops._stream(dev()))
+    fn = _lib.load().naf_enc_stem_tc_f32 if tc else _lib.load().naf_enc_stem_f32
+    rc = fn(ops._ptr(x), sb, sc, sy, sx, ops._ptr(conv.weight), ops._ptr(conv.bias),
+            ops._ptr(out), ops._ptr(part), B, H, W, ks, ops._stream(dev()))
     _lib.check(rc, "stem")
-    assert (out.cpu().double() - want).abs().max().item() <= 1e-5
-    wp = tile_partials(want)
+    tol = 4e-3 * want.abs().max().item() if tc else 1e-5
+    assert (out.cpu().double() - want).abs().max().item() <= tol
+    wp = tile_partials(out.cpu())                      # statistics of the values actually stored
     assert (part.cpu().double().view(B, tiles, 8, 2) - wp).abs().max().item() <= 1e-5 * max(1.0, wp.abs().max().item())
 
 
