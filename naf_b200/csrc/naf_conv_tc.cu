@@ -29,6 +29,9 @@
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
+#ifndef NAF_CONV_PF_DIST
+#define NAF_CONV_PF_DIST 2   // L2 prefetch distance of the producers, in tiles
+#endif
 #ifndef NAF_CONV_EXP
 #define NAF_CONV_EXP 0   // profiling variants (scripts/conv_experiments.sh): 1 no output stores,
 #endif                   // 2 no input loads, 4 no MMAs, 8 weights loaded once, 16 no SiLU
@@ -606,7 +609,7 @@ conv128_ws_kernel(ConvParams p) {
         }
       }
       if (tid < Cfg::HY) {   // L2 prefetch of the tile after next: one bulk prefetch per halo row
-        const int t2 = tile + 2 * int(gridDim.x);
+        const int t2 = tile + NAF_CONV_PF_DIST * int(gridDim.x);
         if (t2 < total) {
           const int b2 = t2 / tiles_per_img, rem2 = t2 - b2 * tiles_per_img;
           const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
@@ -880,7 +883,7 @@ conv128_t_kernel(ConvParams p, int tiles16_x) {
         }
       }
       if (tid < T_HY) {   // L2 prefetch of the tile after next: one bulk prefetch per halo row
-        const int t2 = tile + 2 * int(gridDim.x);
+        const int t2 = tile + NAF_CONV_PF_DIST * int(gridDim.x);
         if (t2 < total) {
           const int b2 = t2 / tiles_per_img, rem2 = t2 - b2 * tiles_per_img;
           const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
