@@ -25,6 +25,8 @@
 // Reference semantics: src/layers/attentions.py:16-29,53-75; RoPE src/layers/rope.py:137-153.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
@@ -87,6 +89,21 @@ __device__ __forceinline__ void ws_split8(const float* x, uint4& hi, uint4& lo) 
   split2_f16(x[2], x[3], hi.y, lo.y);
   split2_f16(x[4], x[5], hi.z, lo.z);
   split2_f16(x[6], x[7], hi.w, lo.w);
+}
+
+// packed fp32x2 helpers (FFMA2): two floats in one 64-bit register
+__device__ __forceinline__ uint64_t ws_pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void ws_unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ws_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
 }
 
 // Division by a launch-constant divisor as multiply-high + shift (exact for the small operands
@@ -350,12 +367,15 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
           if (g + 2 < total_tiles) issue_q();
         }
       }
-      // (b) softmax of tile g
+      // (b) softmax of tile g.  The body is compiled once per row half so that the tap mask
+      // (columns >= K*K are padding) is a compile-time constant: no per-element predicates, and the
+      // padded taps cost neither an exp nor a split.
       const uint32_t ts = tmem + Cfg::kTmemS + s * TP + lane_off;
-      float m = -INFINITY;
-      uint32_t mine[SC];
-      {
-        const int base = half * SC;
+      auto softmax_half = [&](auto half_c) {
+        constexpr int H = decltype(half_c)::value;
+        constexpr int base = H * SC;
+        constexpr int NV = K2 - base < 0 ? 0 : (K2 - base > SC ? SC : K2 - base);   // valid taps of this half
+        uint32_t mine[SC];
         if constexpr (SC % 16 == 0) {
 #pragma unroll
           for (int c0 = 0; c0 < SC; c0 += 16) tmem_ld16(ts + base + c0, *reinterpret_cast<uint32_t(*)[16]>(&mine[c0]));
@@ -364,70 +384,71 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
           for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(ts + base + c0, *reinterpret_cast<uint32_t(*)[8]>(&mine[c0]));
         }
         wait_ld();
+        float m = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < SC; ++j)
-          if (base + j < K2) m = fmaxf(m, __uint_as_float(mine[j]));
-      }
-#if NAF_WS_MEXCH
-      // The two halves of a row exchange their partial maxima through the 16-byte pad of the
-      // row's staging slot (slot [tile parity][half]), and the same named barrier orders the S
-      // reads of both halves before P overwrites the S columns.
-      float* mpad = reinterpret_cast<float*>(stage_out + row * Cfg::kRowBytes + Cfg::kSlabs * Cfg::kRoundCols * 4) + s * 2;
-      mpad[half] = m;
-      fence_before_sync();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      fence_after_sync();
-      m = fmaxf(m, mpad[half ^ 1]);
-#else
-      {
-        // the other half of the row is only read for the row maximum
-        const int other = (1 - half) * SC;
+        for (int j = 0; j < NV; ++j) m = fmaxf(m, __uint_as_float(mine[j]));
+        // The two halves of a row exchange their partial maxima through the 16-byte pad of the
+        // row's staging slot (slot [tile parity][half]), and the same named barrier orders the S
+        // reads of both halves before P overwrites the S columns.
+        float* mpad = reinterpret_cast<float*>(stage_out + row * Cfg::kRowBytes + Cfg::kSlabs * Cfg::kRoundCols * 4) + s * 2;
+        mpad[H] = m;
+        fence_before_sync();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        fence_after_sync();
+        m = fmaxf(m, mpad[H ^ 1]);
+        // e = 2^(s - m) on value pairs (packed fp32x2 subtract and accumulate)
+        const uint64_t one2 = ws_pack2(1.f, 1.f), negm2 = ws_pack2(-m, -m);
+        uint64_t l2 = 0ull;
+        float ev[SC];
 #pragma unroll
-        for (int c0 = 0; c0 < SC; c0 += 8) {
-          uint32_t r[8];
-          tmem_ld8(ts + other + c0, r);
-          wait_ld();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (other + c0 + j < K2) m = fmaxf(m, __uint_as_float(r[j]));
+        for (int j = 0; j < SC; j += 2) {
+          if (j + 1 < NV) {
+            float d0, d1;
+            ws_unpack2(ws_fma2(ws_pack2(__uint_as_float(mine[j]), __uint_as_float(mine[j + 1])), one2, negm2), d0, d1);
+            ev[j] = fast_exp2(d0);
+            ev[j + 1] = fast_exp2(d1);
+            l2 = ws_fma2(ws_pack2(ev[j], ev[j + 1]), one2, l2);
+          } else if (j < NV) {
+            ev[j] = fast_exp2(__uint_as_float(mine[j]) - m);
+            ev[j + 1] = 0.f;
+            l2 = ws_fma2(ws_pack2(ev[j], 0.f), one2, l2);
+          } else {
+            ev[j] = ev[j + 1] = 0.f;
+          }
         }
-      }
-      fence_before_sync();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      fence_after_sync();
-#endif
-      const int tap0 = half * SC;
-      float l = 0.f;
+        float l0, l1;
+        ws_unpack2(l2, l0, l1);
+        // row sum for the epilogue: spare TMEM column, slot [tile & 3][half] (the epilogue may lag
+        // two tiles behind, so two slots would not be enough)
+        tmem_st1(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2 + H, __float_as_uint(l0 + l1));
+        if constexpr (SC % 16 == 0) {
 #pragma unroll
-      for (int j = 0; j < SC; ++j) {
-        const float e = (tap0 + j < K2) ? fast_exp2(__uint_as_float(mine[j]) - m) : 0.f;
-        l += e;
-        mine[j] = __float_as_uint(e);
-      }
-      // row sum for the epilogue: spare TMEM column, slot [tile & 3][half] (the epilogue may lag
-      // two tiles behind, so two slots would not be enough)
-      tmem_st1(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2 + half, __float_as_uint(l));
-      if constexpr (SC % 16 == 0) {
+          for (int c0 = 0; c0 < SC; c0 += 16) {
+            uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int c0 = 0; c0 < SC; c0 += 16) {
-          uint32_t hi[8], lo[8];
+            for (int j = 0; j < 8; ++j) {
+              if (c0 + 2 * j < NV) split2_f16(ev[c0 + 2 * j], ev[c0 + 2 * j + 1], hi[j], lo[j]);
+              else hi[j] = lo[j] = 0u;
+            }
+            tmem_st8(ts + (base + c0) / 2, hi);
+            tmem_st8(ts + TP / 2 + (base + c0) / 2, lo);
+          }
+        } else {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            split2_f16(__uint_as_float(mine[c0 + 2 * j]), __uint_as_float(mine[c0 + 2 * j + 1]), hi[j], lo[j]);
-          tmem_st8(ts + (tap0 + c0) / 2, hi);
-          tmem_st8(ts + TP / 2 + (tap0 + c0) / 2, lo);
+          for (int c0 = 0; c0 < SC; c0 += 8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c0 + 2 * j < NV) split2_f16(ev[c0 + 2 * j], ev[c0 + 2 * j + 1], hi[j], lo[j]);
+              else hi[j] = lo[j] = 0u;
+            }
+            tmem_st4(ts + (base + c0) / 2, hi);
+            tmem_st4(ts + TP / 2 + (base + c0) / 2, lo);
+          }
         }
-      } else {
-#pragma unroll
-        for (int c0 = 0; c0 < SC; c0 += 8) {
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            split2_f16(__uint_as_float(mine[c0 + 2 * j]), __uint_as_float(mine[c0 + 2 * j + 1]), hi[j], lo[j]);
-          tmem_st4(ts + (tap0 + c0) / 2, hi);
-          tmem_st4(ts + TP / 2 + (tap0 + c0) / 2, lo);
-        }
-      }
+      };
+      if (half == 0) softmax_half(std::integral_constant<int, 0>{});
+      else softmax_half(std::integral_constant<int, 1>{});
       wait_st();
       fence_before_sync();
       mbar_arrive(&bar_p_full[s]);   // release: l and P (TMEM) are visible to the consumers
