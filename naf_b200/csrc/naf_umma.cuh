@@ -223,7 +223,14 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 __device__ __forceinline__ void split2_f16(float x0, float x1, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x0, x1);
   const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  // (x0, x1) - (f.x, f.y) as one packed fp32x2 operation: x * 1 + (-f)
+  uint64_t x2, f2, d2;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x2) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(f2) : "f"(-f.x), "f"(-f.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d2) : "l"(x2), "l"(f2));
+  float d0, d1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d2));
+  const __half2 l = __floats2half2_rn(d0, d1);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }

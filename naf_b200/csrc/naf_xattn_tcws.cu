@@ -314,11 +314,16 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
         ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
         ldg8(st, *reinterpret_cast<float(*)[8]>(&sn[0]));
         ldg8(st + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+        // rotation on channel pairs (packed fp32x2): qa' = (a c - b s) qscale, qb' = (b c + a s) qscale
+        const uint64_t qs2 = ws_pack2(qscale, qscale);
 #pragma unroll
-        for (int j = 0; j < P; ++j) {
-          const float a = qa[j], bb = qb[j];
-          qa[j] = (a * c[j] - bb * sn[j]) * qscale;
-          qb[j] = (bb * c[j] + a * sn[j]) * qscale;
+        for (int j = 0; j < P; j += 2) {
+          const uint64_t a2 = ws_pack2(qa[j], qa[j + 1]), b2 = ws_pack2(qb[j], qb[j + 1]);
+          const uint64_t c2 = ws_pack2(c[j], c[j + 1]), s2 = ws_pack2(sn[j], sn[j + 1]);
+          const uint64_t ra = ws_fma2(b2 ^ 0x8000000080000000ull, s2, ws_fma2(a2, c2, 0ull));
+          const uint64_t rb = ws_fma2(a2, s2, ws_fma2(b2, c2, 0ull));
+          ws_unpack2(ws_fma2(ra, qs2, 0ull), qa[j], qa[j + 1]);
+          ws_unpack2(ws_fma2(rb, qs2, 0ull), qb[j], qb[j + 1]);
         }
       } else {
 #pragma unroll
