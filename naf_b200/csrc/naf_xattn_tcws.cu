@@ -541,11 +541,13 @@ xattn_cell_tcws_kernel(naf_xattn_params p, int rh, int rw, int n_items, int vspl
                 *reinterpret_cast<uint4*>(my_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0) + (c * 16 + j) * 2) = pk;
               }
             } else {
+              const uint64_t inv2 = ws_pack2(inv_l, inv_l);
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
-                *reinterpret_cast<float4*>(my_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0) + (c * 16 + j) * 4) =
-                    make_float4(__uint_as_float(r[c & 1][j]) * inv_l, __uint_as_float(r[c & 1][j + 1]) * inv_l,
-                                __uint_as_float(r[c & 1][j + 2]) * inv_l, __uint_as_float(r[c & 1][j + 3]) * inv_l);
+                const uint64_t o01 = ws_fma2(ws_pack2(__uint_as_float(r[c & 1][j]), __uint_as_float(r[c & 1][j + 1])), inv2, 0ull);
+                const uint64_t o23 = ws_fma2(ws_pack2(__uint_as_float(r[c & 1][j + 2]), __uint_as_float(r[c & 1][j + 3])), inv2, 0ull);
+                *reinterpret_cast<uint4*>(my_stage + (Cfg::kDoubleStage ? rd * RC * 4 : 0) + (c * 16 + j) * 4) =
+                    make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
               }
             }
           }
