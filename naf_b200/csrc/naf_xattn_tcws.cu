@@ -52,9 +52,6 @@ constexpr int MMA_WARP = (NFRONT + NBACK) / 32;
 #ifndef NAF_WS_EXP
 #define NAF_WS_EXP 0     // profiling variants: 1 = no output stores, 2 = no q loads, 4 = no window staging after the first item, 8 = 16-byte stores
 #endif
-#ifndef NAF_WS_MEXCH
-#define NAF_WS_MEXCH 1   // row-max exchange between the two row halves: 1 = smem pad, 0 = re-read S from TMEM
-#endif
 
 template <int TP>
 struct WsWindowOf { static constexpr int K = TP == 16 ? 3 : TP == 32 ? 5 : TP == 64 ? 7 : TP == 96 ? 9 : 11; };
