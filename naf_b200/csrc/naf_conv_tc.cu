@@ -29,6 +29,9 @@
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
+#ifndef NAF_CONV_ITEMPIPE
+#define NAF_CONV_ITEMPIPE 1   // producers: 1 = per-item software pipeline (depth NIT/2), 0 = two register batches
+#endif
 #ifndef NAF_CONV_PF_DIST
 #define NAF_CONV_PF_DIST 2   // L2 prefetch distance of the producers, in tiles
 #endif
@@ -591,9 +594,46 @@ conv128_ws_kernel(ConvParams p) {
       }
     };
 
+#if NAF_CONV_ITEMPIPE
+    // Per-item software pipeline of depth DEPTH = NIT / 2: item k is converted DEPTH items after its load
+    // was issued (the batched variant gives a load only one batch of conversions to land, less than an L2
+    // hit takes); the register budget is the same DEPTH x 8 floats.
+    constexpr int NIT = Ws::NIT, DEPTH = NIT / 2;
+    static_assert(NIT % DEPTH == 0, "item pipeline");
+    float v[DEPTH][8];
+    auto load_item = [&](const TileCtx& c, int k, float (&dst)[8]) {
+      const int px = px0 + WS_PXS * k;
+      if (HP % WS_PXS == 0 || px < HP) {
+        const float* src;
+        if (c.interior) {
+          src = c.org + s_goff[px];
+        } else {
+          const int hy = px / WX, hx = px - hy * WX;
+          src = c.img + (int64_t(reflect_clamp(c.y0 + hy - KS / 2, p.H)) * p.W +
+                         reflect_clamp(c.x0 + hx - KS / 2, p.W)) * CC;
+        }
+        ldg_stream8(src, dst);
+      }
+    };
+    auto convert_item = [&](int k, const float (&src)[8], uint8_t* sA) {
+      if (HP % WS_PXS == 0 || px0 + WS_PXS * k < HP) {
+        uint4 hi;
+        uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hp[e] = silu2_f16(fma2(pack2(src[2 * e], src[2 * e + 1]), sc2[e], sh2[e]));
+        *reinterpret_cast<uint4*>(sA + k * (WS_PXS * 16)) = hi;
+      }
+    };
+    TileCtx cur = ctx_of(blockIdx.x);
+    if (cur.valid) {
+#pragma unroll
+      for (int k = 0; k < DEPTH; ++k) load_item(cur, k, v[k]);
+    }
+#else
     float va[BS][8], vb[BS][8];
     TileCtx cur = ctx_of(blockIdx.x);
     if (cur.valid) load_batch(cur, 0, va);
+#endif
     int b_cur = -1, it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -622,6 +662,14 @@ conv128_ws_kernel(ConvParams p) {
       }
       if (it >= 2) mbar_wait(&bar_a_free[buf], ((it >> 1) - 1) & 1);
       uint8_t* sA = smem + buf * Ws::A_BUF + chunk * CS + px0 * 16;
+#if NAF_CONV_ITEMPIPE
+#pragma unroll
+      for (int k = 0; k < NIT; ++k) {
+        convert_item(k, v[k % DEPTH], sA);
+        if (k + DEPTH < NIT) load_item(cur, k + DEPTH, v[k % DEPTH]);
+        else if (nxt.valid) load_item(nxt, k + DEPTH - NIT, v[k % DEPTH]);
+      }
+#else
 #pragma unroll
       for (int j = 0; j < NB; j += 2) {
         load_batch(cur, j + 1, vb);
@@ -630,6 +678,7 @@ conv128_ws_kernel(ConvParams p) {
         else if (nxt.valid) load_batch(nxt, 0, va);
         convert_batch(j + 1, vb, sA);
       }
+#endif
       fence_proxy_async_smem();
       mbar_arrive(&bar_a_full[buf]);
       cur = nxt;
