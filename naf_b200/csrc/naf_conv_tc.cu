@@ -1532,6 +1532,8 @@ int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int6
   int per_img = (sms * 4 + B - 1) / B;   // ~4 CTAs of 128 threads per SM over the whole batch
   if (per_img > tiles) per_img = tiles;
   const dim3 grid(unsigned(per_img), unsigned(B), 1u);
+  prefer_max_shared(stem_conv_kernel<1>);
+  prefer_max_shared(stem_conv_kernel<3>);
   if (KS == 1) stem_conv_kernel<1><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
   else stem_conv_kernel<3><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
   return check_launch("enc_stem");
@@ -1565,6 +1567,8 @@ int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, i
   const int nch = KS == 3 ? 4 : 2;
   const int smem = 2 * nch * 128 * 16 + nch * CC * 16 + WS_NEPI * STAGE_SLOT;
   cudaError_t e;
+  prefer_max_shared(stem_tc_kernel<1>);
+  prefer_max_shared(stem_tc_kernel<3>);
   if (KS == 3) {
     e = cudaFuncSetAttribute(stem_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) stem_tc_kernel<3><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
@@ -1581,6 +1585,7 @@ int launch_enc_gn_coef(const float* part, const float* gamma, const float* beta,
   NAF_REQUIRE(aligned16(coef), NAF_ERR_ALIGNMENT, "enc_gn_coef: 16-byte alignment");
   const int tiles = ((H + TH - 1) / TH) * ((W + TW - 1) / TW);
   NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "enc_gn_coef: batch too large");
+  prefer_max_shared(gn_coef_kernel);
   gn_coef_kernel<<<dim3(unsigned(B), 8u, 1u), 256, 0, st>>>(part, gamma, beta, reinterpret_cast<float2*>(coef), tiles,
                                                           double(H) * W * 16.0, eps);
   return check_launch("enc_gn_coef");

@@ -184,6 +184,8 @@ int launch_rope_kpool(const naf_kpool_params& p, cudaStream_t st) {
   dim3 grid(unsigned(bins_w), unsigned(bins_h), unsigned(p.B));
   const int threads = ((lanes * groups + 31) / 32) * 32;
   const size_t smem = size_t(groups) * lanes * 2 * VEC * sizeof(float);
+  prefer_max_shared(rope_kpool_kernel<4>);
+  prefer_max_shared(rope_kpool_kernel<1>);
   if (VEC == 4)
     rope_kpool_kernel<4><<<grid, threads, smem, st>>>(p, lanes, groups, bins_h, bins_w);
   else

@@ -43,6 +43,7 @@ int launch_pack_nhwc(const float* src, float* dst, int B, int C, int H, int W, i
   NAF_REQUIRE(ptiles < (int64_t(1) << 31) && B <= 65535 && (C + 31) / 32 <= 65535,
               NAF_ERR_UNSUPPORTED, "pack_nhwc: tensor too large for one launch");
   dim3 grid(unsigned(ptiles), unsigned((C + 31) / 32), unsigned(B));
+  prefer_max_shared(pack_nhwc_kernel);
   pack_nhwc_kernel<<<grid, 256, 0, st>>>(src, dst, C, H, W, sb, sc, sh, sw, dstC, dst_off);
   return check_launch("pack_nhwc");
 }
@@ -80,6 +81,7 @@ int launch_concat_bias(const float* a, const float* bias_a, int Ca, const float*
   const int64_t total = npix * ((Ca + Cb) / 4);
   int64_t blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  prefer_max_shared(concat_bias_kernel);
   concat_bias_kernel<<<unsigned(blocks), 256, 0, st>>>(a, bias_a, Ca, b, bias_b, Cb, out, npix);
   return check_launch("concat_bias");
 }
