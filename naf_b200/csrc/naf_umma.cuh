@@ -165,7 +165,23 @@ __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+#ifndef NAF_MBAR_HINT_NS
+#define NAF_MBAR_HINT_NS 0   // > 0: suspend-time hint of try_wait (fewer polls; measured neutral in short runs)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+#if NAF_MBAR_HINT_NS > 0
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(smem_u32(mbar)),
+      "r"(parity), "r"(NAF_MBAR_HINT_NS)
+      : "memory");
+#else
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -177,6 +193,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(mbar)),
       "r"(parity)
       : "memory");
+#endif
 }
 
 // ---- 1-D bulk copy shared -> global (TMA engine, no tensor map needed) -------------------------
