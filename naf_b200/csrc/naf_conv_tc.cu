@@ -1148,8 +1148,11 @@ conv128_t_kernel(ConvParams p, int tiles16_x) {
 // for the whole kernel, and the epilogue is the one of the pipelined conv kernel (bias, GroupNorm
 // partial sums, transpose slab, 128-byte-run stores).  Operands are rounded to fp16 (the TF32 class);
 // the strict fp32 class keeps the SIMT kernel.
+#ifndef NAF_STEM_CTAS
+#define NAF_STEM_CTAS 2   // CTAs per SM of the tensor-core stem (43 KB smem, 256 TMEM columns each)
+#endif
 template <int KS>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WS_THREADS, NAF_STEM_CTAS)
 stem_tc_kernel(ConvParams p, const float* __restrict__ image, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                const float* __restrict__ w) {
   constexpr int NK = 3 * KS * KS;              // 27 or 3
@@ -1563,7 +1566,8 @@ int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, i
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t total = int64_t(B) * p.tiles_y * p.tiles_x;
-  const int grid = int(total < sms ? total : sms);
+  const int64_t cap = int64_t(sms) * NAF_STEM_CTAS;
+  const int grid = int(total < cap ? total : cap);
   const int nch = KS == 3 ? 4 : 2;
   const int smem = 2 * nch * 128 * 16 + nch * CC * 16 + WS_NEPI * STAGE_SLOT;
   cudaError_t e;
