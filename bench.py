@@ -6,16 +6,25 @@
         --master-port P bench.py --gpus N --steps K --warmup W
 
 One "step" = one `NAF.forward(image, features, target_size)` over one batch of synthetic input
-(BASELINE.json configs[1]: DINOv2-B/14, C=768, 448 -> 896, K=7, batch 8 PER GPU; weak scaling).
+(BASELINE.json configs[1] "C2": DINOv2-B/14, C=768, 448 -> 896, K=7, batch 8 PER GPU; weak scaling).
 Rank 0 prints ONE JSON line.  Keys beyond the base contract:
 
-  value        whole NAF.forward (cuDNN encoder + our 3 kernels), inputs resident in HBM
-  hot_path     the same metric for the part this repo replaces (x, features ready -> out ready:
-               pack V + rope/key-pool + attention kernels), and its ms
-  e2e          NAF.forward through the public API from PINNED HOST buffers (H2D of image and
-               features every step, D2H of a result sample every step)
-  roofline     dominant kernel (attention) against the measured HBM peak
-  cpu_baseline the oracle port on the host cores, bounded sample (N=1, rank 0 only)
+  value        whole NAF.forward (tensor-core conv encoder + RoPE/key-pool + attention kernels), inputs
+               resident in HBM
+  hot_path     the same metric for the part SURVEY.md 8(a) scopes (guidance map + features -> out)
+  e2e          NAF.forward through the public host-to-host API from PINNED HOST buffers: H2D of image and
+               features AND D2H of the WHOLE result (19.7 GB at C2) inside the timed region, every step.
+               `e2e_sample` is the same loop reading back only one value per low-res cell (what a consumer
+               that keeps the result on the GPU would copy): labelled, not the headline.
+  roofline     attention kernel, timed live with CUDA events on its launching stream, rated on the bytes
+               the timed launch REALLY moves (guidance map at the encoder resolution, read through
+               replication factors); `frac_8d` rates it on SURVEY.md 8(d)'s formula (x counted at the target
+               resolution); `roofline_rep1` is a second launch with x materialised at the target resolution
+               (where both byte counts coincide)
+  configs      whole-forward ms, attention ms and roofline fraction for the other BASELINE.json configs
+               (C1, C3 [4 images per GPU: B=32 over 8 GPUs], C4, C5)
+  cpu_baseline the UNMODIFIED reference modules (oracle/_ref, NATTEN replaced by oracle/natten_stub.py) on
+               the host cores, bounded sample (N=1, rank 0 only)
 """
 from __future__ import annotations
 
@@ -34,15 +43,18 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     # name: (batch per GPU, C, guidance side, target side, low-res side, K)
-    "C1": (1, 384, 224, 224, 16, 7),
-    "C2": (8, 768, 448, 896, 32, 7),
-    "C3": (4, 1024, 518, 1036, 37, 11),
-    "C4": (2, 768, 336, 1344, 24, 7),
-    "C5": (4, 768, 512, 2048, 32, 7),
+    "C1": (1, 384, 224, 224, 16, 7),      # configs[0]: the reference's own CPU-runnable case
+    "C2": (8, 768, 448, 896, 32, 7),      # configs[1]: the metric's configuration (one GPU)
+    "C3": (4, 1024, 518, 1036, 37, 11),   # configs[2]: batch 32 sharded over 8 GPUs = 4 per GPU
+    "C4": (16, 768, 336, 1344, 24, 7),    # configs[3]: batch 16
+    "C5": (4, 768, 512, 2048, 32, 7),     # configs[4]: batch 4
     # the reference's own benchmark shape (test/test_utils.py:16-25): B=1, C=384, 448 -> 448, lr 28, K=9
     "REF": (1, 384, 448, 448, 28, 9),
 }
 D_GUIDE = 256
+PRECISION = ("attention: fp32 class (split-fp16 operands, 3 tcgen05 passes, fp32 accumulation); conv encoder: "
+             "tf32 class (fp16-rounded operands, fp32 accumulation), i.e. PyTorch's default allow_tf32=True "
+             "that the reference runs with")
 
 
 def ncu_traffic(kernel, workload):
@@ -119,46 +131,66 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
-# ------------------------------------------------------------------------------ CPU baseline
-def cpu_port_step(model_cpu, image, feats, target, K):
-    """One step of the reference algorithm on the host: conv encoder (torch CPU, library code)
-    + the oracle port of RoPE / key pooling / neighbourhood attention."""
-    from oracle import naf_oracle as O
+# ------------------------------------------------------------------- reference on the host cores
+def cpu_sample(workload):
+    """Bounded sample of a workload for the host: ONE image with the same per-pixel work (same C, D, K,
+    ratio r) at 1/16 of the area.  C1 (the reference's own CPU-runnable case) is small enough to run at
+    its full size."""
+    _, C, gi, to, lo, K = WORKLOADS[workload]
+    if workload == "C1":
+        return dict(B=1, C=C, guide=gi, target=to, low=lo, K=K, r=to // lo, full=True)
+    r = to // lo
+    lo_s = max(K, lo // 4)
+    return dict(B=1, C=C, guide=max(1, gi * lo_s // lo), target=lo_s * r, low=lo_s, K=K, r=r, full=False)
 
+
+def reference_cpu_model(K):
+    """(model, kind): the UNMODIFIED reference NAF (oracle/_ref or /root/reference, NATTEN replaced by
+    the stub) when it is available, else the oracle port driven by naf_b200's torch modules."""
+    from oracle import reference_runner as R
+
+    torch.manual_seed(0)
+    if R.available():
+        ns = R.load()
+        return ns.NAF(kernel_size=K).eval(), "reference"
+    import naf_b200
+
+    return naf_b200.NAF(kernel_size=K).eval(), "port"
+
+
+def cpu_step(model, kind, image, feats, target, K):
     with torch.no_grad():
-        x = model_cpu.image_encoder.guidance(image, target)
+        if kind == "reference":
+            return model(image, feats, target)            # the reference's own NAF.forward
+        from oracle import naf_oracle as O
+
+        x = model.image_encoder.guidance(image, target)   # torch-CPU conv encoder + oracle port
         return O.naf_forward(x.contiguous(), feats, 4, 4, K)
 
 
-def cpu_sample(workload):
-    """Bounded sample of the workload for the host: ONE image with the same per-pixel work
-    (same C, D, K, ratio r) at 1/16 of the area."""
-    _, C, gi, to, lo, K = WORKLOADS[workload]
-    r = to // lo
-    lo_s = max(K, lo // 4)
-    return dict(B=1, C=C, guide=max(1, gi * lo_s // lo), target=lo_s * r, low=lo_s, K=K, r=r)
-
-
-def time_cpu_port(workload, steps, warmup):
-    import naf_b200
-
+def time_cpu_reference(workload, steps, warmup):
+    """Mpix/s of the reference's CPU path on a bounded sample of `workload`, all host threads."""
     s = cpu_sample(workload)
-    torch.manual_seed(0)
-    model = naf_b200.NAF(kernel_size=s["K"]).eval()
-    image = torch.randn(s["B"], 3, s["guide"], s["guide"])
-    feats = torch.randn(s["B"], s["C"], s["low"], s["low"])
+    model, kind = reference_cpu_model(s["K"])
+    g = torch.Generator(device="cpu").manual_seed(5)
+    image = torch.randn(s["B"], 3, s["guide"], s["guide"], generator=g)
+    feats = torch.randn(s["B"], s["C"], s["low"], s["low"], generator=g)
     tgt = (s["target"], s["target"])
     for _ in range(warmup):
-        cpu_port_step(model, image, feats, tgt, s["K"])
+        cpu_step(model, kind, image, feats, tgt, s["K"])
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_port_step(model, image, feats, tgt, s["K"])
+        cpu_step(model, kind, image, feats, tgt, s["K"])
     dt = (time.perf_counter() - t0) / max(1, steps)
     mpix = s["B"] * s["target"] ** 2 / 1e6
-    desc = (f"1 image, same per-pixel work at 1/16 area: guidance {s['guide']}^2 -> target "
-            f"{s['target']}^2, features {s['C']}x{s['low']}x{s['low']}, r={s['r']}, K={s['K']}; "
-            f"conv encoder on torch-CPU + oracle port (RoPE, key pool, windowed attention)")
-    return mpix / dt, dt * 1e3, desc
+    what = ("the unmodified reference modules (src/model/naf.py NAF.forward, copied byte for byte into oracle/_ref) "
+            "with NATTEN's na2d_qk/na2d_av replaced by oracle/natten_stub.py (NATTEN is not installable offline)"
+            if kind == "reference" else
+            "conv encoder on torch-CPU + the oracle port (RoPE, key pool, windowed attention); oracle/_ref absent")
+    size = "full size" if s["full"] else "1 image, same per-pixel work at 1/16 of the area"
+    desc = (f"{workload} {size}: guidance {s['guide']}^2 -> target {s['target']}^2, features "
+            f"{s['C']}x{s['low']}x{s['low']}, r={s['r']}, K={s['K']}, batch 1; {what}")
+    return mpix / dt, dt * 1e3, desc, kind
 
 
 def run_reference_arm(args, rank):
@@ -166,34 +198,80 @@ def run_reference_arm(args, rank):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    value, ms, desc = time_cpu_port(args.workload, args.steps, args.warmup)
-    B, C, gi, to, lo, K = WORKLOADS[args.workload]
+    value, ms, desc, kind = time_cpu_reference(args.workload, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": "upsampled Mpix/s", "value": round(value, 5), "unit": "Mpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
-        "cpu_baseline": {"value": round(value, 5), "unit": "Mpix/s", "cores": cores, "kind": "port",
+        "config": workload_config(args.workload, args.gpus, sample=desc),
+        "cpu_baseline": {"value": round(value, 5), "unit": "Mpix/s", "cores": cores, "kind": kind,
                          "sample": desc},
         "e2e": {"value": round(value, 5), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "fps": round(1e3 / ms, 4),
-        "note": "NATTEN (the reference's kernel library) is not installable offline; this arm times "
-                "the oracle port of the reference algorithm on the host cores",
+        "note": "CPU arm: the reference has no CPU kernels of its own for this path (NATTEN is CUDA-first and not "
+                "installable offline), so its unmodified Python modules run over a pure-torch NATTEN stand-in on "
+                "the host cores; each step is a bounded sample of the workload (see config.cpu_sample)",
     }
+    if args.workload != "C1":
+        # BASELINE.json configs[0]: the reference's own CPU-runnable case, at its full size
+        v1, ms1, d1, k1 = time_cpu_reference("C1", max(1, min(args.steps, 3)), 1)
+        line["configs"] = {"C1": {"value": round(v1, 5), "unit": "Mpix/s", "ms_per_step": round(ms1, 2),
+                                  "kind": k1, "cores": cores, "sample": d1}}
     print(json.dumps(line), flush=True)
 
 
-def workload_config(name, n_gpus):
+def workload_config(name, n_gpus, sample=None):
     B, C, gi, to, lo, K = WORKLOADS[name]
-    return {"workload": f"{name}: NAF.forward, guidance {gi}x{gi} -> target {to}x{to}, features "
-                        f"C={C} {lo}x{lo}, K={K}, D=256, 4 heads, batch {B}/GPU",
-            "batch_per_gpu": B, "global_batch": B * n_gpus, "C": C, "guide": gi, "target": to,
-            "low": lo, "K": K, "parallelism": f"batch-sharded x{n_gpus} (no data-path collective)",
-            "l2": "working set per step (x 6.6 GB + out 19.7 GB at C2) >> 126 MB L2: no flush needed"}
+    cfg = {"workload": f"{name}: NAF.forward, guidance {gi}x{gi} -> target {to}x{to}, features "
+                       f"C={C} {lo}x{lo}, K={K}, D=256, 4 heads, batch {B}/GPU",
+           "batch_per_gpu": B, "global_batch": B * n_gpus, "C": C, "guide": gi, "target": to,
+           "low": lo, "K": K, "parallelism": f"batch-sharded x{n_gpus} (no data-path collective)",
+           "l2": "working set per step (x 1.6 GB + out 19.7 GB at C2) >> 126 MB L2: no flush needed",
+           "precision": PRECISION}
+    if sample is not None:
+        cfg["cpu_sample"] = sample
+    return cfg
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+class XattnTimer:
+    """Wraps the one function that enqueues the attention kernel (naf_b200.ops._launch_xattn) with CUDA
+    events recorded on the launching stream.  Lives here: the product carries no instrumentation."""
+
+    def __init__(self, ops):
+        self.ops, self.events, self.orig = ops, [], None
+
+    def __enter__(self):
+        self.orig = self.ops._launch_xattn
+
+        def timed(p, dev):
+            st = torch.cuda.current_stream(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            self.orig(p, dev)
+            e1.record(st)
+            self.events.append((e0, e1))
+
+        self.ops._launch_xattn = timed
+        return self
+
+    def __exit__(self, *exc):
+        self.ops._launch_xattn = self.orig
+
+    def mean_ms(self):
+        return sum(a.elapsed_time(b) for a, b in self.events) / max(1, len(self.events))
+
+
+def xattn_bytes(B, C, to, lo, src):
+    """(real, algorithmic-8d) bytes of one attention launch: real = what the launch moves when the
+    guidance map is stored at `src` x `src` (read once), K and V maps read once, out written once;
+    8d = SURVEY.md 8(d): 4*B*(D*Ho*Wo + C*h*w + C*Ho*Wo)."""
+    real = 4.0 * B * (D_GUIDE * src * src + (D_GUIDE + C) * lo * lo + C * to * to)
+    algo = 4.0 * B * (D_GUIDE * to * to + C * lo * lo + C * to * to)
+    return real, algo
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,11 +279,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tc", "cell_tcws"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tcws"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-d2h", default="sample", choices=["sample", "full"])
+    ap.add_argument("--e2e-d2h", default="full", choices=["full", "sample", "both"],
+                    help="what the e2e step reads back: the whole result (default; `e2e`), one value per "
+                         "low-res cell (`e2e_sample`), or both loops")
+    ap.add_argument("--configs", default="C1,C3,C4,C5",
+                    help="other BASELINE.json configs reported in the `configs` block ('' = none)")
+    ap.add_argument("--config-steps", type=int, default=5)
     ap.add_argument("--graph", type=int, default=0,
-                    help="1: also time NAF.forward replayed as a CUDA graph (naf_b200.GraphedNAF) and run e2e over it; measured no gain at C2 (9.80 vs 9.54 ms): the step is not launch bound")
+                    help="1: also time NAF.forward replayed as a CUDA graph (naf_b200.GraphedNAF)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -222,22 +305,8 @@ def main():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
-    B, C, gi, to, lo, K = WORKLOADS[args.workload]
     algo = {v: k for k, v in _lib.ALGO_NAMES.items()}[args.algo]
-
-    # model: rank 0's random init broadcast to every rank with ONE NCCL broadcast
-    torch.manual_seed(1234 + rank)
-    model = naf_b200.NAF(kernel_size=K).eval().to(dev)
-    model.upsampler.algo = algo
-    n_bcast = ndist.broadcast_module_(model, src=0)
-
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
-    image_h = torch.randn(B, 3, gi, gi, generator=g).pin_memory()
-    feats_h = torch.randn(B, C, lo, lo, generator=g).pin_memory()
-    image = image_h.to(dev)
-    feats = feats_h.to(dev)
-    target = (to, to)
-    r = to // lo
+    peak, peak_src = measured_hbm_peak()
 
     def barrier():
         if world > 1:
@@ -257,6 +326,69 @@ def main():
         barrier()
         return ndist.max_over_ranks(e0.elapsed_time(e1), dev)
 
+    models = {}
+
+    def model_for(K):
+        # rank 0's random init broadcast to every rank with ONE NCCL broadcast
+        if K not in models:
+            torch.manual_seed(1234 + rank)
+            m = naf_b200.NAF(kernel_size=K).eval().to(dev)
+            m.upsampler.algo = algo
+            models[K] = (m, ndist.broadcast_module_(m, src=0))
+        return models[K]
+
+    def roofline_entry(name, B, C, to, lo, K, src, ms, tag=None):
+        real, algo8d = xattn_bytes(B, C, to, lo, src)
+        chosen = ops.select_algo((B, D_GUIDE, to, to), (B, C, lo, lo), 4, K) if args.algo == "auto" else args.algo
+        traffic = ncu_traffic(chosen, name + (f":{tag}" if tag else ""))
+        ach = real / (ms / 1e3) / 1e9
+        return {"bound": "hbm", "kernel": f"xattn ({chosen})", "achieved": round(ach, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                "bytes": int(real), "bytes_what": f"bytes the timed launch moves: guidance map {src}x{src} (read "
+                f"through replication x{to // src}) + K and V maps read once + out written once",
+                "achieved_8d": round(algo8d / (ms / 1e3) / 1e9, 1), "frac_8d": round(algo8d / (ms / 1e3) / 1e9 / peak, 4),
+                "bytes_8d": int(algo8d), "kernel_ms": round(ms, 4), "peak_source": peak_src}
+
+    def run_config(name, steps, warmup):
+        """Whole forward + attention-kernel time of one workload, inputs resident."""
+        B, C, gi, to, lo, K = WORKLOADS[name]
+        model, _ = model_for(K)
+        g = torch.Generator(device="cpu").manual_seed(100 + rank)
+        image = torch.randn(B, 3, gi, gi, generator=g).to(dev)
+        feats = torch.randn(B, C, lo, lo, generator=g).to(dev)
+        sink = {}
+
+        def step():
+            sink.clear()   # the previous result goes back to the allocator first (C4: 88.8 GB per result)
+            sink["out"] = model(image, feats, (to, to))
+
+        with torch.no_grad():
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize(dev)
+            with XattnTimer(ops) as xt:
+                total_ms = timed(step, steps)
+                xattn_ms = xt.mean_ms()
+        sink.clear()
+        ms = total_ms / steps
+        mpix = B * to * to / 1e6 * world
+        src = gi if to % gi == 0 else to
+        return {"workload": workload_config(name, world)["workload"], "global_batch": B * world,
+                "value": round(mpix / (ms / 1e3), 2), "unit": "Mpix/s", "ms_per_step": round(ms, 4),
+                "fps": round(B * world / (ms / 1e3), 2), "steps": steps,
+                "roofline": roofline_entry(name, B, C, to, lo, K, src, xattn_ms)}
+
+    # ============================================================ the metric's workload, in full
+    B, C, gi, to, lo, K = WORKLOADS[args.workload]
+    model, n_bcast = model_for(K)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    image_h = torch.randn(B, 3, gi, gi, generator=g).pin_memory()
+    feats_h = torch.randn(B, C, lo, lo, generator=g).pin_memory()
+    image = image_h.to(dev)
+    feats = feats_h.to(dev)
+    target = (to, to)
+    r = to // lo
+    src = gi if to % gi == 0 else to
     sink = {}
 
     def step_full():
@@ -267,46 +399,26 @@ def main():
     def step_hot():
         sink["out"] = model.upsample_from_guidance(x_holder["x"], feats, rep=x_holder["rep"])
 
-    d2h_buf = {}
     graphed = naf_b200.GraphedNAF(model) if args.graph else None
-    pipe = naf_b200.HostPipeline(graphed if graphed is not None else model, depth=2)
-
-    def e2e_reduce(out):
-        return out if args.e2e_d2h == "full" else out[:, :, r // 2::r, r // 2::r]
-
-    def step_e2e():
-        # public host-to-host API: H2D of this step's inputs, forward, D2H of this step's result;
-        # the transfers run on side streams and overlap the kernels of the neighbouring steps
-        res_h, _ = pipe.step(image_h, feats_h, target, reduce=e2e_reduce)
-        d2h_buf["buf"] = res_h
-
-    def step_e2e_serial():
-        img = image_h.to(dev, non_blocking=True)
-        ft = feats_h.to(dev, non_blocking=True)
-        out = model(img, ft, target)
-        res = e2e_reduce(out)
-        if "ser" not in d2h_buf:
-            d2h_buf["ser"] = torch.empty(res.shape, dtype=res.dtype).pin_memory()
-        d2h_buf["ser"].copy_(res, non_blocking=True)
-        sink["out"] = out
+    fwd = graphed if graphed is not None else model
+    out_bytes = 4 * B * C * to * to
 
     with torch.no_grad():
-        # ---- warm-up (also builds cuDNN plans and the caching-allocator pools)
+        # ---- warm-up (builds tables, packed weights and the caching-allocator pools)
         for _ in range(args.warmup):
             step_full()
         torch.cuda.synchronize(dev)
         sink.clear()
 
         # ---- timed: whole NAF.forward, inputs resident in HBM
-        ops.XATTN_EVENTS = []
         launches0 = ops.launch_count()
         sampler = ClockSampler(local)
         sampler.start()
-        total_ms = timed(step_full, args.steps)
+        with XattnTimer(ops) as xt:
+            total_ms = timed(step_full, args.steps)
+            xattn_ms = xt.mean_ms()
         clocks = sampler.finish()
         launches = ops.launch_count() - launches0
-        events, ops.XATTN_EVENTS = ops.XATTN_EVENTS, None
-        xattn_ms = sum(a.elapsed_time(b) for a, b in events) / max(1, len(events))
         sink.clear()
 
         # ---- timed: the replaced part only (x, features ready -> out ready)
@@ -315,36 +427,78 @@ def main():
             step_hot()
         hot_ms = timed(step_hot, args.steps) / args.steps
         sink.clear()
+
+        # ---- timed: the attention launch with the guidance map materialised at the TARGET resolution
+        # (the shape every reference eval caller produces; SURVEY.md 8d asks for both image shapes)
+        rep1 = None
+        if x_holder["rep"] != (1, 1):
+            ry, rx = x_holder["rep"]
+            x_full = x_holder["x"].repeat_interleave(ry, 2).repeat_interleave(rx, 3).contiguous(
+                memory_format=torch.channels_last)
+
+            def step_rep1():
+                sink["out"] = model.upsample_from_guidance(x_full, feats, rep=(1, 1))
+
+            for _ in range(2):
+                step_rep1()
+            with XattnTimer(ops) as xt1:
+                timed(step_rep1, max(3, args.steps // 2))
+                rep1 = roofline_entry(args.workload, B, C, to, lo, K, to, xt1.mean_ms(), tag="rep1")
+            sink.clear()
+            del x_full
         x_holder.clear()
 
-        # ---- timed: end to end from pinned host buffers through the public API
         graph_ms = None
         if graphed is not None:
-            # the forward as a CUDA-graph replay (same kernels, no per-launch host work), inputs resident
             def step_graph():
                 sink["out"] = graphed(image, feats, target)
             for _ in range(3):
                 step_graph()
             graph_ms = timed(step_graph, args.steps) / args.steps
             sink.clear()
-        for _ in range(2):
-            step_e2e()
-        pipe.drain()
-        e2e_ms = timed(step_e2e, args.steps, finish=pipe.drain) / args.steps
-        d2h_bytes = d2h_buf["buf"].numel() * 4
-        for _ in range(2):
-            step_e2e_serial()
-        e2e_serial_ms = timed(step_e2e_serial, args.steps) / args.steps
+
+        # ---- timed: end to end from pinned host buffers through the public host-to-host API
+        def e2e_loop(reduce, host_ring_bytes=0):
+            pipe = naf_b200.HostPipeline(fwd, depth=2, host_ring_bytes=host_ring_bytes)
+            got = {}
+
+            def step():
+                got["res"] = pipe.step(image_h, feats_h, target, reduce=reduce)[0]
+
+            for _ in range(2):
+                step()
+            pipe.drain()
+            torch.cuda.synchronize(dev)
+            ms = timed(step, args.steps, finish=pipe.drain) / args.steps
+            nbytes = got["res"].numel() * got["res"].element_size() if reduce is not None else out_bytes
+            del pipe
+            return ms, nbytes
+
+        e2e_full = e2e_sample = None
+        if args.e2e_d2h in ("full", "both"):
+            try:
+                ms, nb = e2e_loop(None)
+                how = "one pinned host buffer of the result size"
+            except RuntimeError as exc:   # pinned allocation of the full result refused by the host: ring
+                ms, nb = e2e_loop(None, host_ring_bytes=1 << 30)
+                how = f"pinned ring of 2 x 1 GiB (full-size pinned buffer failed: {str(exc)[:80]})"
+            e2e_full = (ms, nb, how)
+        if args.e2e_d2h in ("sample", "both") or e2e_full is None:
+            e2e_sample = e2e_loop(lambda out: out[:, :, r // 2::r, r // 2::r])
         sink.clear()
+        torch.cuda.empty_cache()
 
     ms_per_step = total_ms / args.steps
     mpix_step = B * to * to / 1e6 * world          # whole job, all ranks
     value = mpix_step / (ms_per_step / 1e3)
-    algo_bytes = 4.0 * B * (D_GUIDE * to * to + C * lo * lo + C * to * to)  # per launch, per GPU
-    peak, peak_src = measured_hbm_peak()
-    achieved = algo_bytes / (xattn_ms / 1e3) / 1e9
-    chosen = ops.select_algo((B, D_GUIDE, to, to), (B, C, lo, lo), 4, K) if args.algo == "auto" else args.algo
-    traffic = ncu_traffic(chosen, args.workload)
+    h2d = int(image_h.numel() * 4 + feats_h.numel() * 4)
+    api = ("naf_b200.HostPipeline.step (pinned host in -> pinned host out; H2D / D2H on side streams overlap the "
+           "neighbouring steps' kernels)" + (" over naf_b200.GraphedNAF" if graphed is not None else ""))
+
+    def e2e_entry(ms, nbytes, what):
+        return {"value": round(mpix_step / (ms / 1e3), 3), "unit": "Mpix/s", "ms": round(ms, 4),
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(nbytes), "d2h": what, "api": api,
+                "d2h_gbs": round(nbytes / (ms / 1e3) / 1e9, 2)}
 
     line = {
         "metric": "upsampled Mpix/s", "value": round(value, 3), "unit": "Mpix/s", "n_gpus": world,
@@ -354,38 +508,50 @@ def main():
         "fps": round(B * world / (ms_per_step / 1e3), 3),
         "hot_path": {"value": round(mpix_step / (hot_ms / 1e3), 3), "unit": "Mpix/s", "ms": round(hot_ms, 4),
                      "what": "encoder-resolution guidance map + features resident -> out: pack V, RoPE+key-pool, attention"},
-        "e2e": {"value": round(mpix_step / (e2e_ms / 1e3), 3), "unit": "Mpix/s", "ms": round(e2e_ms, 4),
-                "h2d_bytes_per_step": int(image_h.numel() * 4 + feats_h.numel() * 4),
-                "d2h_bytes_per_step": int(d2h_bytes),
-                "d2h": ("full output" if args.e2e_d2h == "full" else
-                        "result sample: the upsampled features at every cell centre (B,C,h,w)"),
-                "api": "naf_b200.HostPipeline.step (pinned host in -> pinned host out; H2D/D2H on side "
-                       "streams overlap the neighbouring steps' kernels)" +
-                       (" over naf_b200.GraphedNAF (CUDA-graph replay of the forward)" if graphed is not None else ""),
-                "serial_ms": round(e2e_serial_ms, 4)},
-        "graph_replay": ({"value": round(mpix_step / (graph_ms / 1e3), 3), "unit": "Mpix/s", "ms": round(graph_ms, 4),
-                          "what": "NAF.forward replayed as one CUDA graph (naf_b200.GraphedNAF), inputs resident"}
-                         if graph_ms else None),
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": f"xattn ({chosen})", "achieved": round(achieved, 1),
-                     "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                     "traffic": traffic,
-                     # the same launch rated on the DRAM bytes ncu measured for it (the guidance map is read
-                     # at the encoder resolution through replication factors: less than the algorithmic x)
-                     "achieved_on_traffic": (round(traffic / (xattn_ms / 1e3) / 1e9, 1) if traffic else None),
-                     "frac_on_traffic": (round(traffic / (xattn_ms / 1e3) / 1e9 / peak, 4) if traffic else None),
-                     "kernel_ms": round(xattn_ms, 4), "algorithmic_bytes": int(algo_bytes),
-                     "peak_source": peak_src},
+        "roofline": roofline_entry(args.workload, B, C, to, lo, K, src, xattn_ms),
         "clocks": clocks,
         "weights_broadcast_elems": int(n_bcast),
     }
+    if rep1 is not None:
+        line["roofline_rep1"] = rep1
+    if e2e_full is not None:
+        line["e2e"] = e2e_entry(e2e_full[0], e2e_full[1], f"the WHOLE result (B,Ho,Wo,C) fp32, every step; {e2e_full[2]}")
+        if e2e_sample is not None:
+            line["e2e_sample"] = e2e_entry(e2e_sample[0], e2e_sample[1],
+                                           "NOT host-to-host: only the upsampled features at every cell centre (B,C,h,w) are read back")
+    else:
+        line["e2e"] = e2e_entry(e2e_sample[0], e2e_sample[1],
+                                "SAMPLE ONLY (--e2e-d2h sample): the upsampled features at every cell centre (B,C,h,w); "
+                                "the result itself stays on the GPU")
+    if graph_ms:
+        line["graph_replay"] = {"value": round(mpix_step / (graph_ms / 1e3), 3), "unit": "Mpix/s", "ms": round(graph_ms, 4)}
+
+    # ============================================================ the other BASELINE.json configs
+    names = [n for n in args.configs.split(",") if n and n != args.workload]
+    if names:
+        line["configs"] = {}
+        for name in names:
+            try:
+                with torch.no_grad():
+                    line["configs"][name] = run_config(name, args.config_steps, 3)
+            except Exception as exc:   # e.g. out of memory for a big batch on a shared GPU: report, go on
+                line["configs"][name] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+            torch.cuda.empty_cache()
+        if "C3" in line["configs"] and "error" not in line["configs"]["C3"]:
+            line["configs"]["C3"]["note"] = (f"BASELINE.json configs[2] = batch 32 sharded over 8 GPUs = 4 images per GPU; "
+                                             f"this run: {world} GPU(s), global batch {4 * world}")
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        v, ms, desc = time_cpu_port(args.workload, steps=1, warmup=1)
-        line["cpu_baseline"] = {"value": round(v, 5), "unit": "Mpix/s", "cores": cores, "kind": "port",
+        v, ms, desc, kind = time_cpu_reference(args.workload, steps=2, warmup=1)
+        line["cpu_baseline"] = {"value": round(v, 5), "unit": "Mpix/s", "cores": cores, "kind": kind,
                                 "sample": desc, "ms_per_sample": round(ms, 1)}
+        if args.workload != "C1":
+            v1, ms1, d1, k1 = time_cpu_reference("C1", steps=2, warmup=1)
+            line["cpu_baseline"]["C1_full_size"] = {"value": round(v1, 5), "unit": "Mpix/s", "ms": round(ms1, 1),
+                                                    "kind": k1, "sample": d1}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NAF_ABI_VERSION 2
+#define NAF_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define NAF_API __attribute__((visibility("default")))
@@ -50,6 +50,11 @@ NAF_API int naf_abi_version(void);
 
 /* Message for the last non-OK status returned on this host thread ("" if none). */
 NAF_API const char* naf_last_error(void);
+
+/* Number of kernels this library has launched since it was loaded whose family name starts with
+ * `prefix` (NULL or "" = all): "xattn", "enc_conv", "rope_kpool", "pack_nhwc", ...  Host-side
+ * counter incremented after every successful launch; used by bench.py's `gpu_launches`. */
+NAF_API unsigned long long naf_launch_count(const char* prefix);
 
 /* 1 if the library was compiled with the tcgen05/TMEM tensor-core path, 0 if SIMT only. */
 NAF_API int naf_has_tensor_path(void);
@@ -146,7 +151,8 @@ typedef struct naf_xattn_params {
 
 enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1 };
 
-enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2, NAF_ALGO_CELL_TC = 3,
+enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2,
+       NAF_ALGO_CELL_TC = 3 /* removed in ABI v3 (non-pipelined tensor-core kernel); requests fail with NAF_ERR_UNSUPPORTED */,
        NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline */ };
 
 NAF_API int naf_xattn_fwd_f32(const naf_xattn_params* p, void* stream);

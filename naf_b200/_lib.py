@@ -12,11 +12,12 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NAF_B200_LIB") or os.path.join(_HERE, "csrc", "libnaf_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 NAF_OK, NAF_ERR_BAD_SHAPE, NAF_ERR_UNSUPPORTED, NAF_ERR_WINDOW, NAF_ERR_ALIGNMENT, NAF_ERR_NULL, NAF_ERR_CUDA = range(7)
 ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS = range(5)
-ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TC: "cell_tc", ALGO_CELL_TCWS: "cell_tcws"}
+# (3 was the non-pipelined tensor-core kernel, removed in ABI v3; the value stays reserved)
+ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TCWS: "cell_tcws"}
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -64,6 +65,7 @@ EXPORTS = {
     "naf_abi_version": (C.c_int, []),
     "naf_last_error": (C.c_char_p, []),
     "naf_has_tensor_path": (C.c_int, []),
+    "naf_launch_count": (C.c_ulonglong, [C.c_char_p]),
     "naf_pack_nhwc_f32": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_int64, C.c_int64, C.c_int64, C.c_int64, _fp]),
     "naf_pack_nhwc_slab_f32": (C.c_int, [_fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,

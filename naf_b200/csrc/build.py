@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libnaf_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 SOURCES = ["naf_abi.cu", "naf_pack.cu", "naf_kpool.cu", "naf_xattn_generic.cu", "naf_xattn_simt.cu",
-           "naf_xattn_tc.cu", "naf_xattn_tcws.cu", "naf_encoder.cu", "naf_conv_tc.cu"]
+           "naf_xattn_tcws.cu", "naf_encoder.cu", "naf_conv_tc.cu"]
 HEADERS = ["naf_common.cuh", "naf_umma.cuh", os.path.join(ROOT, "include", "naf_b200.h")]
 
 
@@ -26,13 +26,24 @@ def nvcc_path() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
-def _digest() -> str:
+def _read(f: str) -> bytes:
+    path = f if os.path.isabs(f) else os.path.join(HERE, f)
+    with open(path, "rb") as fh:
+        return fh.read()
+
+
+def _digest(sources=None, verbose: bool = False) -> str:
+    """Hash of what an object (one source) or the library (all sources) is built from: the source(s),
+    every header, this script and the compiler flags."""
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS + [os.path.abspath(__file__)]:
-        path = f if os.path.isabs(f) else os.path.join(HERE, f)
-        with open(path, "rb") as fh:
-            h.update(fh.read())
+    for f in list(SOURCES if sources is None else sources) + HEADERS + [os.path.abspath(__file__)]:
+        h.update(_read(f))
+    h.update(" ".join(_flags(verbose) + EXTRA_FLAGS).encode())
     return h.hexdigest()
+
+
+#: extra nvcc flags from the environment (experiment switches such as -DNAF_WS_EXP=1)
+EXTRA_FLAGS = os.environ.get("NAF_NVCC_FLAGS", "").split()
 
 
 def _flags(verbose: bool = False) -> list[str]:
@@ -46,11 +57,13 @@ def _flags(verbose: bool = False) -> list[str]:
 
 def command(verbose: bool = False) -> list[str]:
     """The equivalent single nvcc invocation (what build() does, file by file in parallel)."""
-    return [nvcc_path()] + _flags(verbose) + ["-shared", "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
+    return [nvcc_path()] + _flags(verbose) + EXTRA_FLAGS + ["-shared", "-o", LIB] + [os.path.join(HERE, s) for s in SOURCES]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    dig = _digest()
+    """Incremental: an object is recompiled only when its source, a header, the flags or this script
+    changed (per-object stamp files under _obj/); the library is relinked when any object changed."""
+    dig = _digest(verbose=verbose)
     if not force and os.path.isfile(LIB) and os.path.isfile(STAMP):
         with open(STAMP) as fh:
             if fh.read().strip() == dig:
@@ -63,14 +76,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        res = subprocess.run([nvcc] + _flags(verbose) + ["-c", os.path.join(HERE, src), "-o", obj],
+        stamp = obj + ".stamp"
+        d = _digest([src], verbose)
+        if not force and os.path.isfile(obj) and os.path.isfile(stamp):
+            with open(stamp) as fh:
+                if fh.read().strip() == d:
+                    return src, obj, None
+        res = subprocess.run([nvcc] + _flags(verbose) + EXTRA_FLAGS + ["-c", os.path.join(HERE, src), "-o", obj],
                              capture_output=True, text=True)
+        if res.returncode == 0:
+            with open(stamp, "w") as fh:
+                fh.write(d)
         return src, obj, res
 
     with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
         results = list(pool.map(compile_one, SOURCES))
     failed = False
     for src, _, res in results:
+        if res is None:
+            continue
         if verbose or res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
         failed |= res.returncode != 0

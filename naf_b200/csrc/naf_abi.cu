@@ -1,6 +1,10 @@
 // extern "C" entry points of libnaf_b200.so: argument validation, algorithm selection, error
 // reporting.  See include/naf_b200.h for the contract of every function.
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
 
 #include "naf_common.cuh"
 
@@ -19,11 +23,66 @@ int fail(naf_status code, const char* fmt, ...) {
   return static_cast<int>(code);
 }
 
+// kernel launches performed by this library since it was loaded, per kernel family (the `what` of
+// check_launch); read through naf_launch_count().  Counting lives here, not in the Python layer.
+static std::mutex g_count_mu;
+static std::map<std::string, unsigned long long> g_counts;
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess)
     return fail(NAF_ERR_CUDA, "%s: CUDA error %d (%s)", what, int(e), cudaGetErrorString(e));
+  {
+    std::lock_guard<std::mutex> lock(g_count_mu);
+    ++g_counts[what];
+  }
   return NAF_OK;
+}
+
+unsigned long long launch_count(const char* prefix) {
+  std::lock_guard<std::mutex> lock(g_count_mu);
+  unsigned long long n = 0;
+  const size_t len = prefix ? strlen(prefix) : 0;
+  for (const auto& kv : g_counts)
+    if (len == 0 || kv.first.compare(0, len, prefix) == 0) n += kv.second;
+  return n;
+}
+
+int device_sm_count() {
+  constexpr int kMaxDev = 64;
+  static int cache[kMaxDev] = {0};   // benign race: every writer stores the same value
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < kMaxDev && cache[dev] > 0) return cache[dev];
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < kMaxDev) cache[dev] = sms;
+  return sms;
+}
+
+cudaError_t ensure_dyn_smem_impl(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> configured;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  int& have = configured[std::make_pair(func, dev)];
+  if (bytes <= have) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
+}
+
+void prefer_max_shared_impl(const void* func) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, bool> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  bool& d = done[std::make_pair(func, dev)];
+  if (d) return;
+  cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  d = true;
 }
 
 static int validate_xattn(const naf_xattn_params& p) {
@@ -74,10 +133,9 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
     if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
     return -fail(NAF_ERR_UNSUPPORTED, "xattn: pipelined tensor-core cell kernel unsupported: %s", why);
   }
-  if (p.algo == NAF_ALGO_CELL_TC) {
-    if (xattn_cell_tc_supported(p, &why)) return NAF_ALGO_CELL_TC;
-    return -fail(NAF_ERR_UNSUPPORTED, "xattn: tensor-core cell kernel unsupported: %s", why);
-  }
+  if (p.algo == NAF_ALGO_CELL_TC)
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: the non-pipelined tensor-core kernel (algo 3) was removed in ABI v3; "
+                                       "use NAF_ALGO_CELL_TCWS");
   if (p.algo == NAF_ALGO_CELL_SIMT) {
     if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
     return -fail(NAF_ERR_UNSUPPORTED, "xattn: SIMT cell kernel unsupported: %s", why);
@@ -85,7 +143,6 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
   if (p.algo != NAF_ALGO_AUTO) return -fail(NAF_ERR_UNSUPPORTED, "xattn: unknown algo %d", p.algo);
   (void)explain;
   if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
-  if (xattn_cell_tc_supported(p, &why)) return NAF_ALGO_CELL_TC;
   if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
   return NAF_ALGO_GENERIC;
 }
@@ -99,6 +156,8 @@ extern "C" {
 int naf_abi_version(void) { return NAF_ABI_VERSION; }
 
 const char* naf_last_error(void) { return last_error_buffer(); }
+
+unsigned long long naf_launch_count(const char* prefix) { return launch_count(prefix); }
 
 int naf_has_tensor_path(void) {
 #ifdef NAF_WITH_TC
@@ -167,8 +226,6 @@ int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
   switch (algo) {
     case NAF_ALGO_CELL_TCWS:
       return launch_xattn_cell_tcws(p, st);
-    case NAF_ALGO_CELL_TC:
-      return launch_xattn_cell_tc(p, st);
     case NAF_ALGO_CELL_SIMT:
       return launch_xattn_cell_simt(p, st);
     default:

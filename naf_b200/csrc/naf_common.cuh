@@ -15,6 +15,7 @@ namespace naf {
 char* last_error_buffer();
 int fail(naf_status code, const char* fmt, ...);
 int check_launch(const char* what);
+unsigned long long launch_count(const char* prefix);
 
 #define NAF_REQUIRE(cond, code, ...)          \
   do {                                        \
@@ -25,9 +26,21 @@ int check_launch(const char* what);
 // hot kernel of the step runs with ~200 KB of dynamic shared memory; a small kernel launched between two
 // of them with the default (L1-heavy) carveout makes the SMs reconfigure their L1/shared split twice,
 // which drains the machine (measured: ~1 ms of idle GPU per C2 step over 21 launches).
+void prefer_max_shared_impl(const void* func);   // once per (kernel, device)
 template <class Kernel>
 inline void prefer_max_shared(Kernel k) {
-  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  prefer_max_shared_impl(reinterpret_cast<const void*>(k));
+}
+
+// ---- launch-time device queries, cached (the latency-bound shapes pay for every runtime call) ----
+// SM count of the current device (queried once per device).
+int device_sm_count();
+// One-time dynamic shared-memory opt-in per (kernel, device); raises the limit when a later call
+// needs more.  Function attributes are per device, so the cache is keyed on both.
+cudaError_t ensure_dyn_smem_impl(const void* func, int bytes);
+template <class Kernel>
+inline cudaError_t ensure_dyn_smem(Kernel k, int bytes) {
+  return ensure_dyn_smem_impl(reinterpret_cast<const void*>(k), bytes);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -125,8 +138,6 @@ int launch_rope_kpool(const naf_kpool_params& p, cudaStream_t st);
 int launch_xattn_generic(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_simt(const naf_xattn_params& p, cudaStream_t st);
-bool xattn_cell_tc_supported(const naf_xattn_params& p, const char** why);
-int launch_xattn_cell_tc(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_tcws(const naf_xattn_params& p, cudaStream_t st);
 int launch_concat_bias(const float* a, const float* bias_a, int Ca, const float* b, const float* bias_b,

@@ -778,369 +778,6 @@ conv128_ws_kernel(ConvParams p) {
   if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 256);
 }
 
-#if NAF_CONV_NPROD == 256   // the operand-swapped variant is written for 256 producer threads
-// ---- 3x3, 1 pass, operands swapped: D[cout][pixel] = W[cout][cin] . Act[pixel][cin]^T, N = 256 pixels ----
-// Experiment kept as an alternative (passes = -3): a 128x128x16 MMA reads 8 KB of operands in 64 math
-// cycles and conv128_ws_kernel<3> refills 288 KB of weights per 128-pixel tile, so shared-memory
-// bandwidth looked like its limiter.  Here the weights are the M operand and a 32x8 = 256-pixel tile
-// is the N operand: one 128x256x16 MMA reads 12 KB for twice the math, and a tap's weights serve 256
-// pixels.  Measured: the same 0.535 ms per layer -- clock64 timelines of the three roles
-// (-DNAF_CONV_TIMING) show the MMA thread waiting ~30-40 % of the time for the PRODUCERS (global-load
-// latency + SiLU chains on 8 warps), not for operands.  Shared memory then holds the activated halo tile in two
-// 64-channel halves (ring of 3 half tiles: the producers fill one while the tensor core reads another),
-// a 4-slot ring of 16 KB weight granules (one tap, 64 input channels) and a 32-pixel transpose slab.
-// The accumulator (128 channel lanes x 256 pixel columns, double buffered = all 512 TMEM columns) is
-// drained by 4 warps, thread = output channel, transposed through the slab to pixel-major stores.
-namespace {
-constexpr int T_TH = 32, T_TW = 8;                         // 256-pixel tile
-constexpr int T_HY = T_TH + 2, T_WX = T_TW + 2, T_HP = T_HY * T_WX;   // halo 34 x 10 = 340 pixels
-constexpr int T_CS = T_HP * 16 + 16;                       // chunk plane stride (bank pad)
-constexpr int T_HALF = 8 * T_CS;                           // one 64-channel half tile: 43648 B
-constexpr int T_ASLOTS = 3, T_WSLOTS = 4;
-constexpr int T_WGRAN = 8 * CC * 16;                       // one tap x 64 input channels: 16 KB
-constexpr int T_SLAB_ROW = CC * 4 + 16;                    // one pixel of the transpose slab
-constexpr int T_SLAB = 32 * T_SLAB_ROW;
-constexpr int T_W_OFF = T_ASLOTS * T_HALF;
-constexpr int T_SLAB_OFF = T_W_OFF + T_WSLOTS * T_WGRAN;
-constexpr int T_SMEM = T_SLAB_OFF + T_SLAB;
-constexpr int T_NIT = (T_HP + 31) / 32;                    // halo pixels per producer thread and half: 11
-static_assert(T_HALF % 128 == 0 && T_SMEM <= 227 * 1024 - 2048, "conv128_t smem");
-}  // namespace
-
-__global__ void __launch_bounds__(WS_THREADS, 1)
-conv128_t_kernel(ConvParams p, int tiles16_x) {
-  constexpr int KS = 3, NT = 9;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_a_full[T_ASLOTS], bar_a_free[T_ASLOTS], bar_w_full[T_WSLOTS], bar_w_free[T_WSLOTS];
-  __shared__ uint64_t bar_acc_full[2], bar_acc_free[2];
-  __shared__ uint32_t tmem_base_s;
-  __shared__ int s_goff[T_NIT * 32];
-
-  uint8_t* sW = smem + T_W_OFF;
-  uint8_t* sSlab = smem + T_SLAB_OFF;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int tiles_per_img = p.tiles_y * p.tiles_x;     // 32x8 tiles here
-  const int total = p.B * tiles_per_img;
-
-  if (warp == WS_MMA_WARP) tmem_alloc(&tmem_base_s, 512);
-  if (tid == 0) {
-    for (int s = 0; s < T_ASLOTS; ++s) {
-      mbar_init(&bar_a_full[s], WS_NPROD);
-      mbar_init(&bar_a_free[s], 1);
-    }
-    for (int s = 0; s < T_WSLOTS; ++s) {
-      mbar_init(&bar_w_full[s], 1);
-      mbar_init(&bar_w_free[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_acc_full[s], 1);
-      mbar_init(&bar_acc_free[s], WS_NEPI);
-    }
-    fence_mbar_init();
-  }
-  for (int px = tid; px < T_NIT * 32; px += WS_THREADS) {
-    const int q = px < T_HP ? px : T_HP - 1, hy = q / T_WX, hx = q - hy * T_WX;
-    s_goff[px] = (hy * p.W + hx) * CC;
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-
-  if (warp < WS_NPROD / 32) {
-    // ============================================================================== PRODUCERS
-    // thread = (chunk c of the 8 in a 64-channel half, pixel slot ps); items px = ps + 32 k.
-    // Per tile 6 register batches (3 per half: 4 + 4 + 3 pixels) alternate between va and vb.
-    const int c8 = tid & 7, ps = tid >> 3;
-    auto ctx_of = [&](int tile) {
-      TileCtx c;
-      c.valid = tile < total;
-      c.b = 0; c.y0 = 0; c.x0 = 0; c.interior = false; c.img = p.in; c.org = p.in;
-      if (c.valid) {
-        c.b = tile / tiles_per_img;
-        const int rem = tile - c.b * tiles_per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        c.y0 = ty * T_TH;
-        c.x0 = tx * T_TW;
-        c.interior = c.y0 >= 1 && c.y0 + T_TH + 1 <= p.H && c.x0 >= 1 && c.x0 + T_TW + 1 <= p.W;
-        c.img = p.in + int64_t(c.b) * p.H * p.W * CC + c8 * 8;
-        c.org = c.img + (int64_t(c.y0 - 1) * p.W + (c.x0 - 1)) * CC;
-      }
-      return c;
-    };
-    // batch j of a tile: half kh = j / 3, pixels k = (j % 3) * 4 .. (+4, or +3 for the last)
-    auto load_batch = [&](const TileCtx& c, int j, float (&v)[4][8]) {
-      const int kh = j / 3, k0 = (j % 3) * 4;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = k0 + kk;
-        const int px = ps + 32 * k;
-        if (k < T_NIT && px < T_HP) {
-          const float* src;
-          if (c.interior) {
-            src = c.org + s_goff[px] + kh * 64;
-          } else {
-            const int hy = px / T_WX, hx = px - hy * T_WX;
-            src = c.img + (int64_t(reflect_clamp(c.y0 + hy - 1, p.H)) * p.W + reflect_clamp(c.x0 + hx - 1, p.W)) * CC + kh * 64;
-          }
-          ldg_stream8(src, v[kk]);
-        }
-      }
-    };
-    uint64_t sc2[2][4], sh2[2][4];   // GroupNorm {scale, shift} pairs of this thread's 8 channels, per half
-    auto convert_batch = [&](int j, float (&v)[4][8], uint8_t* sA) {
-      const int kh = j / 3, k0 = (j % 3) * 4;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const int k = k0 + kk;
-        const int px = ps + 32 * k;
-        if (k < T_NIT && px < T_HP) {
-          uint4 hi;
-          uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint64_t t2 = fma2(pack2(v[kk][2 * e], v[kk][2 * e + 1]), sc2[kh][e], sh2[kh][e]);
-            hp[e] = silu2_f16(t2);
-          }
-          *reinterpret_cast<uint4*>(sA + px * 16) = hi;
-        }
-      }
-    };
-
-    float va[4][8], vb[4][8];
-    TileCtx cur = ctx_of(blockIdx.x);
-    if (cur.valid) load_batch(cur, 0, va);
-    int b_cur = -1, it = 0;
-#ifdef NAF_CONV_TIMING
-    long long pt_wait = 0, pt_conv = 0, pt_load = 0, pt_fence = 0, pt0 = clock64(), ptt;
-#define PTIMED(acc, stmt) { ptt = clock64(); stmt; acc += clock64() - ptt; }
-#else
-#define PTIMED(acc, stmt) { stmt; }
-#endif
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const TileCtx nxt = ctx_of(tile + int(gridDim.x));
-      if (cur.b != b_cur) {
-        b_cur = cur.b;
-#pragma unroll
-        for (int kh = 0; kh < 2; ++kh) {
-          const float4* cp = reinterpret_cast<const float4*>(p.coef + cur.b * CC + kh * 64 + c8 * 8);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 c = __ldg(cp + j);
-            sc2[kh][j] = pack2(c.x, c.z);
-            sh2[kh][j] = pack2(c.y, c.w);
-          }
-        }
-      }
-      if (tid < T_HY) {   // L2 prefetch of the tile after next: one bulk prefetch per halo row
-        const int t2 = tile + NAF_CONV_PF_DIST * int(gridDim.x);
-        if (t2 < total) {
-          const int b2 = t2 / tiles_per_img, rem2 = t2 - b2 * tiles_per_img;
-          const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
-          const int yy = reflect_clamp(ty2 * T_TH - 1 + tid, p.H);
-          const int span = T_WX < p.W ? T_WX : p.W;
-          int xs = tx2 * T_TW - 1;
-          xs = xs < 0 ? 0 : (xs > p.W - span ? p.W - span : xs);
-          bulk_prefetch_l2(p.in + ((int64_t(b2) * p.H + yy) * p.W + xs) * CC, uint32_t(span) * CC * 4);
-        }
-      }
-      const int u0 = 2 * it;   // sequence number of this tile's first half tile
-      // ---- half 0
-      {
-        const int u = u0, slot = u % T_ASLOTS;
-        if (u >= T_ASLOTS) PTIMED(pt_wait, mbar_wait(&bar_a_free[slot], ((u / T_ASLOTS) - 1) & 1))
-        uint8_t* sA = smem + slot * T_HALF + c8 * T_CS;
-        PTIMED(pt_load, load_batch(cur, 1, vb))
-        PTIMED(pt_conv, convert_batch(0, va, sA))
-        PTIMED(pt_load, load_batch(cur, 2, va))
-        PTIMED(pt_conv, convert_batch(1, vb, sA))
-        PTIMED(pt_load, load_batch(cur, 3, vb))
-        PTIMED(pt_conv, convert_batch(2, va, sA))
-        PTIMED(pt_fence, fence_proxy_async_smem(); mbar_arrive(&bar_a_full[slot]))
-      }
-      // ---- half 1
-      {
-        const int u = u0 + 1, slot = u % T_ASLOTS;
-        if (u >= T_ASLOTS) PTIMED(pt_wait, mbar_wait(&bar_a_free[slot], ((u / T_ASLOTS) - 1) & 1))
-        uint8_t* sA = smem + slot * T_HALF + c8 * T_CS;
-        PTIMED(pt_load, load_batch(cur, 4, va))
-        PTIMED(pt_conv, convert_batch(3, vb, sA))
-        PTIMED(pt_load, load_batch(cur, 5, vb))
-        PTIMED(pt_conv, convert_batch(4, va, sA))
-        if (nxt.valid) PTIMED(pt_load, load_batch(nxt, 0, va))
-        PTIMED(pt_conv, convert_batch(5, vb, sA))
-        PTIMED(pt_fence, fence_proxy_async_smem(); mbar_arrive(&bar_a_full[slot]))
-      }
-      cur = nxt;
-    }
-#ifdef NAF_CONV_TIMING
-    if (blockIdx.x == 3 && tid == 0)
-      printf("conv128_t producer thread 0 (CTA 3, %d tiles): total %lld clk; waiting a_free %lld, convert (incl. load wait) %lld, load issue %lld, fence+arrive %lld\n",
-             it, (long long)(clock64() - pt0), pt_wait, pt_conv, pt_load, pt_fence);
-#endif
-  } else if (warp < WS_MMA_WARP) {
-    // =============================================================================== EPILOGUE
-    // thread = output channel (TMEM lane); 8 rounds of 32 pixel columns per tile, each transposed
-    // through the slab so that a warp stores one whole pixel slab (512 contiguous bytes) at a time.
-    const int ew = warp - WS_NPROD / 32, et = tid - WS_NPROD;
-    const int ch = ew * 32 + lane;
-    const uint32_t lane_off = uint32_t(ew * 32) << 16;
-    const float bias = p.bias ? p.bias[ch] : 0.f;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const int b = tile / tiles_per_img, rem = tile - b * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int y0 = ty * T_TH, x0 = tx * T_TW;
-#ifdef NAF_CONV_TIMING
-      static __device__ long long e_wait_dbg, e_tot_dbg;
-      const long long et0 = clock64();
-#endif
-      mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
-#ifdef NAF_CONV_TIMING
-      if (blockIdx.x == 3 && et == 0) { e_wait_dbg += clock64() - et0; }
-#endif
-      fence_after_sync();
-      float s = 0.f, ss = 0.f;
-#pragma unroll 1
-      for (int rd = 0; rd < 8; ++rd) {
-        uint32_t r[32];
-        tmem_ld32(tmem + lane_off + buf * 256 + rd * 32, r);
-        wait_ld();
-        if (rd == 7) {   // the accumulator is in registers: the MMAs of tile it+2 may overwrite it
-          fence_before_sync();
-          mbar_arrive(&bar_acc_free[buf]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int pp = rd * 32 + j;                       // pixel of the tile: row pp / 8, column pp % 8
-          const float v = __uint_as_float(r[j]) + bias;
-          if (y0 + (pp >> 3) < p.H && x0 + (pp & 7) < p.W) {   // warp-uniform
-            s += v;
-            ss = fmaf(v, v, ss);
-          }
-          *reinterpret_cast<float*>(sSlab + j * T_SLAB_ROW + ch * 4) = v;
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = i * 4 + ew, pp = rd * 32 + j;
-          const int y = y0 + (pp >> 3), x = x0 + (pp & 7);
-          const float4 o = *reinterpret_cast<const float4*>(sSlab + j * T_SLAB_ROW + lane * 16);
-          if (y < p.H && x < p.W)
-            stg_stream(p.out + ((int64_t(b) * p.H + y) * p.W + x) * p.out_pix_stride + p.out_ch_off + lane * 4, o);
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
-      if (p.part) {
-        // group = 16 adjacent channels = 16 adjacent lanes
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        }
-        // partial-sum slots are indexed by 16x8 tiles (what gn_coef_kernel sums over): this 32x8
-        // tile fills the slot of its upper half and zeroes the slot of its lower half
-        const int64_t slot_hi = (int64_t(b) * ((p.H + 15) / 16) + 2 * ty) * tiles16_x + tx;
-        if ((lane & 15) == 0) {
-          const int g = ew * 2 + (lane >> 4);
-          p.part[slot_hi * 16 + g * 2] = s;
-          p.part[slot_hi * 16 + g * 2 + 1] = ss;
-          if (2 * ty + 1 < (p.H + 15) / 16) {
-            p.part[(slot_hi + tiles16_x) * 16 + g * 2] = 0.f;
-            p.part[(slot_hi + tiles16_x) * 16 + g * 2 + 1] = 0.f;
-          }
-        }
-      }
-#ifdef NAF_CONV_TIMING
-      if (blockIdx.x == 3 && et == 0) {
-        e_tot_dbg += clock64() - et0;
-        if (tile + int(gridDim.x) >= total) {
-          printf("conv128_t epilogue thread 0 (CTA 3): total %lld clk; waiting acc_full %lld\n", e_tot_dbg, e_wait_dbg);
-          e_tot_dbg = 0; e_wait_dbg = 0;
-        }
-      }
-#endif
-    }
-  } else if (warp == WS_MMA_WARP) {
-    // ============================================================================= MMA ISSUER
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(128, 256, false, false);
-      const uint32_t w_base = smem_u32(sW);
-      uint32_t wslot = 0, wphase = 0;
-      int it = 0;
-#ifdef NAF_CONV_TIMING
-      long long t_acc = 0, t_a = 0, t_w = 0, t_issue = 0, t0 = clock64(), tt;
-#define TIMED(acc, stmt) { tt = clock64(); stmt; acc += clock64() - tt; }
-#else
-#define TIMED(acc, stmt) { stmt; }
-#endif
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        if (it >= 2) TIMED(t_acc, mbar_wait(&bar_acc_free[buf], ((it >> 1) - 1) & 1))
-        const uint32_t tD = tmem + buf * 256;
-#pragma unroll 1
-        for (int kh = 0; kh < 2; ++kh) {
-          const int u = 2 * it + kh, slot = u % T_ASLOTS;
-          TIMED(t_a, mbar_wait(&bar_a_full[slot], (u / T_ASLOTS) & 1))
-          fence_after_sync();
-          const uint32_t a_base = smem_u32(smem + slot * T_HALF);
-#pragma unroll 1
-          for (int tap = 0; tap < NT; ++tap) {
-            TIMED(t_w, mbar_wait(&bar_w_full[wslot], wphase))
-            const int dy = tap / KS, dx = tap - dy * KS;
-            const uint32_t act = a_base + (dy * T_WX + dx) * 16;
-            const uint32_t wgt = w_base + wslot * T_WGRAN;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint64_t dw = make_desc(wgt + kk * 2 * (CC * 16), CC * 16, 128);        // M operand: weights
-              const uint64_t da = make_desc(act + kk * 2 * T_CS, T_CS, T_WX * 16);          // N operand: pixels
-              mma_f16_ss(tD, dw, da, idesc, (kh | tap | kk) != 0);
-            }
-            commit(&bar_w_free[wslot]);
-            if (++wslot == T_WSLOTS) { wslot = 0; wphase ^= 1; }
-          }
-          commit(&bar_a_free[slot]);
-        }
-        commit(&bar_acc_full[buf]);
-      }
-#ifdef NAF_CONV_TIMING
-      if (blockIdx.x == 3) {
-        // wait for the last accumulator so the total covers the whole pipeline
-        printf("conv128_t MMA thread (CTA 3, %d tiles): total %lld clk; waiting acc_free %lld, a_full %lld, w_full %lld\n",
-               it, (long long)(clock64() - t0), t_acc, t_a, t_w);
-      }
-      (void)t_issue;
-#endif
-    }
-    __syncwarp();
-  } else {
-    // ================================================================================= LOADER
-    if (lane == 0) {
-      uint32_t wslot = 0, fphase = 1;
-      bool first_round = true;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-#pragma unroll 1
-        for (int g = 0; g < 2 * NT; ++g) {
-          const int kh = g / NT, tap = g - kh * NT;
-          if (!first_round) mbar_wait(&bar_w_free[wslot], fphase);
-          mbar_expect_tx(&bar_w_full[wslot], T_WGRAN);
-          // packed image: [tap][plane hi|lo][chunk 16][n 128][16 B]; chunks 8 kh .. 8 kh + 7 of the hi plane
-          bulk_load(sW + wslot * T_WGRAN, p.wpack + (size_t(tap) * 2 * NCHUNK + kh * 8) * (CC * 16), T_WGRAN,
-                    &bar_w_full[wslot]);
-          if (++wslot == T_WSLOTS) { wslot = 0; fphase ^= 1; first_round = false; }
-        }
-      }
-    }
-    __syncwarp();
-  }
-
-  fence_before_sync();
-  __syncthreads();
-  if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 512);
-}
-
-#endif
-
 // ---- stem on the tensor core (1 pass): Conv2d(3 -> 128, KS, reflect) as a 128 x 128 x {16, 32} GEMM ----
 // The SIMT stem below is FMA bound (0.40 ms for the 3x3 stem at C2, 3x the time its 822 MB of output
 // needs).  Here the producers build the im2col row of every pixel directly in the K-major operand layout
@@ -1440,46 +1077,22 @@ template <int KS>
 int launch_conv_ws(const ConvParams& p, cudaStream_t st) {
   using Ws = WsConvCfg<KS>;
   auto kern = conv128_ws_kernel<KS>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws::SMEM);
+  cudaError_t e = ensure_dyn_smem(kern, Ws::SMEM);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sm_count();
   const int64_t total = int64_t(p.B) * p.tiles_y * p.tiles_x;
   const int grid = int(total < sms ? total : sms);
   kern<<<grid, WS_THREADS, Ws::SMEM, st>>>(p);
   return check_launch("enc_conv(ws)");
 }
 
-int launch_conv_t(ConvParams p, cudaStream_t st) {
-#if NAF_CONV_NPROD != 256
-  (void)p; (void)st;
-  return fail(NAF_ERR_UNSUPPORTED, "enc_conv: the operand-swapped kernel is not part of this build");
-#else
-  cudaError_t e = cudaFuncSetAttribute(conv128_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-  if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int tiles16_x = p.tiles_x;
-  p.tiles_y = (p.H + T_TH - 1) / T_TH;     // 32x8 tiles
-  p.tiles_x = (p.W + T_TW - 1) / T_TW;
-  const int64_t total = int64_t(p.B) * p.tiles_y * p.tiles_x;
-  const int grid = int(total < sms ? total : sms);
-  conv128_t_kernel<<<grid, WS_THREADS, T_SMEM, st>>>(p, tiles16_x);
-  return check_launch("enc_conv(t)");
-#endif
-}
-
 template <int KS, int PASSES>
 int launch_conv(const ConvParams& p, cudaStream_t st) {
   using Cfg = ConvCfg<KS, PASSES>;
   auto kern = conv128_tc_kernel<KS, PASSES>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  cudaError_t e = ensure_dyn_smem(kern, Cfg::SMEM);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sm_count();
   const int64_t total = int64_t(p.B) * p.tiles_y * p.tiles_x;
   const int64_t cap = int64_t(sms) * Cfg::CTAS_PER_SM;
   const int grid = int(total < cap ? total : cap);
@@ -1493,7 +1106,7 @@ int launch_enc_conv(const float* in, const float* coef, const void* wpack, const
                     int64_t out_pix_stride, int out_ch_off, float* part, int B, int H, int W, int KS,
                     int passes, cudaStream_t st) {
   NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_conv: kernel size %d (1 or 3)", KS);
-  NAF_REQUIRE(passes == 1 || passes == 3 || passes == -1 || passes == -3, NAF_ERR_UNSUPPORTED, "enc_conv: passes must be 1 or 3");
+  NAF_REQUIRE(passes == 1 || passes == 3, NAF_ERR_UNSUPPORTED, "enc_conv: passes must be 1 or 3");
   NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_conv: reflect padding needs H, W >= 2");
   NAF_REQUIRE(aligned32(in) && aligned16(wpack) && aligned16(out) && aligned16(coef) &&
                   out_pix_stride % 4 == 0 && out_ch_off % 4 == 0 && out_pix_stride >= out_ch_off + CC,
@@ -1514,12 +1127,9 @@ int launch_enc_conv(const float* in, const float* coef, const void* wpack, const
   p.W = W;
   p.tiles_y = (H + TH - 1) / TH;
   p.tiles_x = (W + TW - 1) / TW;
-  // passes: 1 = 1-pass pipelined kernel, 3 = split-fp16 kernel; kept for A/B measurements:
-  // -1 = 1 pass on the non-pipelined kernel, -3 = 1 pass on the operand-swapped N=256 kernel (3x3 only;
-  // measured equal to the pipelined M=128 kernel: 0.535 ms per layer at C2, so the simpler one is the default)
-  if (KS == 1) return (passes == 1 || passes == -3) ? launch_conv_ws<1>(p, st) : passes == 3 ? launch_conv<1, 3>(p, st) : launch_conv<1, 1>(p, st);
-  if (passes == -3) return launch_conv_t(p, st);
-  return passes == 1 ? launch_conv_ws<3>(p, st) : passes == 3 ? launch_conv<3, 3>(p, st) : launch_conv<3, 1>(p, st);
+  // passes: 1 = 1-pass pipelined kernel (TF32 class), 3 = split-fp16 kernel (fp32 class)
+  if (KS == 1) return passes == 1 ? launch_conv_ws<1>(p, st) : launch_conv<1, 3>(p, st);
+  return passes == 1 ? launch_conv_ws<3>(p, st) : launch_conv<3, 3>(p, st);
 }
 
 int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
@@ -1529,9 +1139,7 @@ int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int6
   NAF_REQUIRE(aligned16(out) && (!bias || aligned16(bias)), NAF_ERR_ALIGNMENT, "enc_stem: 16-byte alignment");
   NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "enc_stem: batch too large");
   const int tiles_y = (H + TH - 1) / TH, tiles_x = (W + TW - 1) / TW, tiles = tiles_y * tiles_x;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sm_count();
   int per_img = (sms * 4 + B - 1) / B;   // ~4 CTAs of 128 threads per SM over the whole batch
   if (per_img > tiles) per_img = tiles;
   const dim3 grid(unsigned(per_img), unsigned(B), 1u);
@@ -1562,9 +1170,7 @@ int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, i
   p.tiles_y = (H + TH - 1) / TH;
   p.tiles_x = (W + TW - 1) / TW;
   NAF_REQUIRE(int64_t(B) * p.tiles_y * p.tiles_x < (int64_t(1) << 27), NAF_ERR_UNSUPPORTED, "enc_stem_tc: too many tiles");
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = device_sm_count();
   const int64_t total = int64_t(B) * p.tiles_y * p.tiles_x;
   const int64_t cap = int64_t(sms) * NAF_STEM_CTAS;
   const int grid = int(total < cap ? total : cap);
@@ -1574,10 +1180,10 @@ int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, i
   prefer_max_shared(stem_tc_kernel<1>);
   prefer_max_shared(stem_tc_kernel<3>);
   if (KS == 3) {
-    e = cudaFuncSetAttribute(stem_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = ensure_dyn_smem(stem_tc_kernel<3>, smem);
     if (e == cudaSuccess) stem_tc_kernel<3><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
   } else {
-    e = cudaFuncSetAttribute(stem_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    e = ensure_dyn_smem(stem_tc_kernel<1>, smem);
     if (e == cudaSuccess) stem_tc_kernel<1><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
   }
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_stem_tc: smem opt-in failed: %s", cudaGetErrorString(e));

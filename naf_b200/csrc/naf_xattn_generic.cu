@@ -109,12 +109,9 @@ int launch_xattn_generic(const naf_xattn_params& p, cudaStream_t st) {
               smem);
   NAF_REQUIRE(int64_t(p.B) * p.h * p.w < (int64_t(1) << 31), NAF_ERR_UNSUPPORTED,
               "xattn(generic): feature map too large");
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(xattn_generic_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (smem > 48 * 1024) {   // per (kernel, device) opt-in, cached in ensure_dyn_smem
+    cudaError_t e = ensure_dyn_smem(xattn_generic_kernel, int(smem));
     if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn(generic): smem opt-in failed: %s", cudaGetErrorString(e));
-    configured = smem;
   }
   const int64_t items = int64_t(p.B) * p.Ho * p.Wo * p.heads;
   int64_t blocks = (items + kGenericWarps - 1) / kGenericWarps;

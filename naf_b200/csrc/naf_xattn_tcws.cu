@@ -697,12 +697,10 @@ int launch_ws(const naf_xattn_params& p, int vsplit, cudaStream_t st) {
     return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tcws): tile %dx%d/%d does not fit", TP, DV, ROUNDS);
   } else {
     auto kern = xattn_cell_tcws_kernel<TP, DV, ROUNDS>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemTotal);
+    cudaError_t e = ensure_dyn_smem(kern, Cfg::kSmemTotal);
     if (e != cudaSuccess)
       return fail(NAF_ERR_CUDA, "xattn(cell-tcws): smem opt-in failed: %s", cudaGetErrorString(e));
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sm_count();
     const int64_t items = int64_t(p.B) * p.h * p.w * p.heads * vsplit;
     const int grid = int(items < sms ? items : sms);
     const int rh = p.Ho / p.h, rw = p.Wo / p.w;

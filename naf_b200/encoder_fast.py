@@ -1,14 +1,23 @@
-"""Fast forward of the guidance conv encoder (first step).
+"""Forward of the guidance conv encoder on our kernels.
 
 The reference's `encoder()` (src/layers/convolutions.py:70-95) is a stem conv followed by EncBlocks
-(GroupNorm -> SiLU -> conv -> GroupNorm -> SiLU -> conv, reflect padding, no residual).  Run through
-ATen it costs ~51 ms at 8x3x448x448 of which < 5 ms are the convolutions: the rest is a 64-CTA
-GroupNorm reduction, separate normalise / SiLU / reflection-pad / bias-add passes and cuDNN layout
-conversions.  This module keeps the convolutions on cuDNN (channels_last, no bias) and replaces
-everything between them by two of our kernels per GroupNorm (`naf_gn_stats_f32`,
-`naf_gn_silu_apply_f32`: bias of the previous conv + GroupNorm + SiLU + reflect pad of the next
-conv in one pass) on pixel-major activations.  The result is bit-for-bit the same math (GroupNorm
-moments are accumulated in double), so the golden parity tests of the whole module still apply.
+(GroupNorm -> SiLU -> conv -> GroupNorm -> SiLU -> conv, reflect padding, no residual).  Two paths:
+
+* `forward_tc` (the one `NAF.forward` takes for the reference-default 128-channel branches): the whole
+  stack on tcgen05 kernels of libnaf_b200.so -- stem conv, per EncBlock half one GroupNorm-coefficient
+  kernel and ONE fused GroupNorm+SiLU+reflect-pad+conv+bias kernel (naf_conv_tc.cu).  No library
+  convolution is called.
+* `forward` (other channel widths): cuDNN convolutions (channels_last, no bias) with everything
+  between them replaced by two of our kernels per GroupNorm (`naf_gn_stats_f32`,
+  `naf_gn_silu_apply_f32`).
+
+Precision classes follow `torch.backends.cudnn.allow_tf32` (see `conv_passes`): operands rounded to
+fp16 (10-bit mantissa like TF32, but fp16's 5-bit exponent: |x| <= 65504, and values below 6e-5 lose
+bits -- the GroupNorm-normalised activations, the weights and an ImageNet-normalised image (the
+reference's calling convention, evaluation/eval_seg_probing.py:98) sit far inside that range; raw
+un-normalised 16-bit imagery does not and must use the strict class), or split-fp16 operands with
+fp32-class accuracy and the exact fp32 SIMT stem (`allow_tf32 = False`, no range restriction beyond
+fp32's for the image).
 """
 from __future__ import annotations
 
@@ -80,7 +89,6 @@ def groupnorm_silu(y, prev_bias, norm, pad: int):
         rc = lib.naf_gn_silu_apply_f32(ops._ptr(y), ops._ptr(prev_bias), ops._ptr(norm.weight), ops._ptr(norm.bias),
                                        ops._ptr(sums), ops._ptr(out), B, H, W, Cn, G, float(norm.eps), pad, st)
         _lib.check(rc, "naf_gn_silu_apply_f32")
-    ops.LAUNCHES["groupnorm"] = ops.LAUNCHES.get("groupnorm", 0) + 2
     return out
 
 
@@ -176,7 +184,6 @@ def forward_tc(seq, image, out=None, ch_off=0, passes=None):
                                       passes, st)
             _lib.check(rc, "naf_enc_conv_f32")
             y = dst
-    ops.LAUNCHES["encoder_tc"] = ops.LAUNCHES.get("encoder_tc", 0) + 1 + 2 * len(layers)
     return out
 
 

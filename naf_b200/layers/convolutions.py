@@ -2,9 +2,10 @@
 
 Same module tree -- and therefore the same `state_dict` keys and shapes -- as the reference's
 `encoder()` / `EncBlock` (src/layers/convolutions.py:9-95): a stem conv followed by pre-norm
-blocks GroupNorm -> SiLU -> conv -> GroupNorm -> SiLU -> conv with reflect padding.  These are
-ATen/cuDNN library ops in the reference and stay library ops here (SURVEY.md 8f ranks native
-sm_100a kernels for them as the next row after the attention path).
+blocks GroupNorm -> SiLU -> conv -> GroupNorm -> SiLU -> conv with reflect padding.  The modules
+hold the parameters (and run as plain torch modules on CPU tensors, in training mode and for
+non-default widths); on CUDA `NAF.forward` evaluates the reference-default stacks through the fused
+tcgen05 kernels of `naf_b200/encoder_fast.py:forward_tc` instead of calling these modules.
 """
 from __future__ import annotations
 

@@ -119,6 +119,27 @@ def rope_rotate(x: torch.Tensor, heads: int, periods: torch.Tensor) -> torch.Ten
     return out.permute(0, 1, 3, 2).reshape(B, D, H, W)
 
 
+def rope_rotate_pixels(xv: torch.Tensor, ys, xs, H: int, W: int, heads: int, periods: torch.Tensor) -> torch.Tensor:
+    """Rotation of individual pixels: xv (N, D) holds the un-rotated vectors of the pixels
+    (ys[i], xs[i]) of an H x W map -> (N, D).  Same formulas as `rope_tables` / `rope_rotate`
+    (/root/reference/src/layers/rope.py:99-105,139-153) evaluated only where asked, so that the
+    full-size spot checks need no (H*W, D_head) table."""
+    N, D = xv.shape
+    dh = D // heads
+    dt = xv.dtype
+    ys = torch.as_tensor(ys, dtype=dt)
+    xs = torch.as_tensor(xs, dtype=dt)
+    coords = torch.stack([(ys + 0.5) / H, (xs + 0.5) / W], dim=-1)      # arange(0.5, H) / H
+    coords = 2.0 * coords - 1.0
+    ang = 2 * math.pi * coords[:, :, None] / periods.to(dt)[None, None, :]
+    ang = ang.flatten(1, 2).tile(2)                                      # (N, dh)
+    cos, sin = torch.cos(ang)[:, None, :], torch.sin(ang)[:, None, :]
+    v = xv.reshape(N, heads, dh)
+    a, b = v[..., : dh // 2], v[..., dh // 2 :]
+    rot = torch.cat([-b, a], dim=-1)
+    return (v * cos + rot * sin).reshape(N, D)
+
+
 def key_pool(q: torch.Tensor, h: int, w: int) -> torch.Tensor:
     return F.adaptive_avg_pool2d(q, output_size=(h, w))
 

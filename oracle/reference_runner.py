@@ -1,10 +1,12 @@
-"""TEST INFRASTRUCTURE ONLY -- load the UNMODIFIED reference modules from /root/reference.
+"""TEST INFRASTRUCTURE ONLY -- load the UNMODIFIED reference modules.
 
-Works only in the build container (``/root/reference`` does not exist on the GPU box).  It is
-used by `oracle/gen_golden.py` to produce the committed fixtures under ``tests/golden/`` and by
-the ``-m "not gpu"`` tests that pin `oracle/naf_oracle.py` against the reference (skipped when
-the reference tree is absent).  The reference's NATTEN dependency is replaced by
-`oracle/natten_stub.py` (see that file for what is and is not pinned).
+Looked up, in this order: $NAF_REFERENCE_ROOT, `oracle/_ref/` (the byte-for-byte copy made by
+`oracle/build_ref.py`, git-ignored, which travels to the GPU box with the gpurun snapshot -- so
+bench.py never reads /root/reference at run time) and /root/reference (the build container).  Used by `oracle/gen_golden*.py` to produce the committed
+fixtures under ``tests/golden/``, by the ``-m "not gpu"`` tests that pin `oracle/naf_oracle.py`
+against the reference, and by `bench.py`'s reference arm / `cpu_baseline` leg.  The reference's
+NATTEN dependency is replaced by `oracle/natten_stub.py` (see that file for what is and is not
+pinned).
 """
 from __future__ import annotations
 
@@ -13,11 +15,26 @@ import io
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("NAF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("NAF_REFERENCE_ROOT"), os.path.join(_HERE, "_ref"), "/root/reference"]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "src", "model", "naf.py")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "src", "model", "naf.py"))
+
+
+def is_vendored_copy() -> bool:
+    return os.path.abspath(REFERENCE_ROOT) == os.path.join(_HERE, "_ref")
 
 
 _cache = {}

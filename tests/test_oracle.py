@@ -160,3 +160,15 @@ def test_encoder_resolution_rule():
     assert O.image_encoder_resolution(448, 448, 56, 56) == (224, 224)
     assert O.image_encoder_resolution(448, 448, 112, 112) == (448, 448)
     assert O.image_encoder_resolution(224, 224, 448, 448) == (224, 224)
+
+
+def test_per_pixel_rope_equals_the_map_rotation():
+    """`rope_rotate_pixels` (used by the full-size GPU spot checks) == `rope_rotate` on the same pixels."""
+    import numpy as np
+    x = torch.from_numpy(np.random.RandomState(3).standard_normal((1, 256, 9, 13)).astype(np.float32))
+    per = O.rope_periods(64)
+    full = O.rope_rotate(x, 4, per)
+    ys, xs = [0, 8, 4, 2], [0, 12, 7, 11]
+    got = O.rope_rotate_pixels(torch.stack([x[0, :, y, xx] for y, xx in zip(ys, xs)]), ys, xs, 9, 13, 4, per)
+    want = torch.stack([full[0, :, y, xx] for y, xx in zip(ys, xs)])
+    assert torch.equal(got, want)
