@@ -157,6 +157,59 @@ enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2,
 
 NAF_API int naf_xattn_fwd_f32(const naf_xattn_params* p, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Backward of the cross-scale neighbourhood attention.
+ * Replaces what autograd does to reference legacy_attention (src/layers/attentions.py:16-29) through
+ * NATTEN's backward functionals, as train.py:136 and test/backward_speed.py:51-64 run it.
+ * q, k, v, tables, strides, rep and scale exactly as passed to the forward (nothing else is saved for
+ * backward: the probabilities are recomputed); dout is dL/dout, (B,Ho,Wo,C) contiguous fp32.  Outputs:
+ *   dq (B,Ho,Wo,D) contiguous : gradient w.r.t. the ROTATED queries (= w.r.t. q when no rope tables);
+ *   dk (B,h,w,D), dv (B,h,w,C): zeroed by the call, then accumulated (scatter-add over the windows).
+ * algo: NAF_ALGO_AUTO (cell kernel for integer ratios, else generic), NAF_ALGO_GENERIC, NAF_ALGO_CELL_SIMT.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct naf_xattn_bwd_params {
+  const float* q;
+  const float* k;
+  const float* v;
+  const float* dout;
+  float* dq;
+  float* dk;
+  float* dv;
+  const int32_t* row_tap;
+  const int32_t* col_tap;
+  const float* cos_y;
+  const float* sin_y;
+  const float* cos_x;
+  const float* sin_x;
+  int32_t B, D, C, heads, Ho, Wo, h, w, K;
+  float scale;
+  int64_t q_stride_b, q_stride_y, q_stride_x; /* elements */
+  int32_t algo;
+  int32_t rep_y, rep_x;
+} naf_xattn_bwd_params;
+
+NAF_API int naf_xattn_bwd_f32(const naf_xattn_bwd_params* p, void* stream);
+
+/* Backward of naf_rope_kpool_f32 (reference: autograd through RoPE.forward, src/layers/rope.py:155-174,
+ * and adaptive_avg_pool2d in KeyEncoder.forward, src/model/naf.py:63-69):
+ *   dx = R^T ( dq + sum over the pooling bins holding the pixel of dk_bin / |bin| )
+ * dq (B,Ho,Wo,D) gradient w.r.t. the rotated map (NULL = zero), dk (B,h,w,D) gradient w.r.t. the pooled
+ * keys (NULL = none), dx (B,Ho,Wo,D) contiguous, may alias dq.  Tables as in the forward (all NULL: no
+ * rotation).  x is taken at the target resolution (replication factors 1). */
+typedef struct naf_kpool_bwd_params {
+  const float* dq;
+  const float* dk;
+  float* dx;
+  const float* cos_y;
+  const float* sin_y;
+  const float* cos_x;
+  const float* sin_x;
+  int32_t B, D, Ho, Wo, h, w;
+  int32_t rope_heads;
+} naf_kpool_bwd_params;
+
+NAF_API int naf_rope_kpool_bwd_f32(const naf_kpool_bwd_params* p, void* stream);
+
 /* Which NAF_ALGO_* would AUTO select for these parameters (no launch).  Negative = -naf_status. */
 NAF_API int naf_xattn_select_algo(const naf_xattn_params* p);
 

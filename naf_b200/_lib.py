@@ -58,6 +58,36 @@ class XAttnParams(C.Structure):
         self.rep_y = self.rep_x = 1
 
 
+class XAttnBwdParams(C.Structure):
+    """Mirror of `naf_xattn_bwd_params` (include/naf_b200.h)."""
+
+    _fields_ = [
+        ("q", _fp), ("k", _fp), ("v", _fp), ("dout", _fp), ("dq", _fp), ("dk", _fp), ("dv", _fp),
+        ("row_tap", _fp), ("col_tap", _fp),
+        ("cos_y", _fp), ("sin_y", _fp), ("cos_x", _fp), ("sin_x", _fp),
+        ("B", C.c_int32), ("D", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32),
+        ("Ho", C.c_int32), ("Wo", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("K", C.c_int32),
+        ("scale", C.c_float),
+        ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
+        ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32),
+    ]
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.rep_y = self.rep_x = 1
+
+
+class KPoolBwdParams(C.Structure):
+    """Mirror of `naf_kpool_bwd_params` (include/naf_b200.h)."""
+
+    _fields_ = [
+        ("dq", _fp), ("dk", _fp), ("dx", _fp),
+        ("cos_y", _fp), ("sin_y", _fp), ("cos_x", _fp), ("sin_x", _fp),
+        ("B", C.c_int32), ("D", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("h", C.c_int32), ("w", C.c_int32), ("rope_heads", C.c_int32),
+    ]
+
+
 DTYPE_F32, DTYPE_BF16 = 0, 1
 
 #: every symbol include/naf_b200.h declares: name -> (restype, argtypes)
@@ -73,6 +103,8 @@ EXPORTS = {
     "naf_rope_kpool_f32": (C.c_int, [C.POINTER(KPoolParams), _fp]),
     "naf_xattn_fwd_f32": (C.c_int, [C.POINTER(XAttnParams), _fp]),
     "naf_xattn_select_algo": (C.c_int, [C.POINTER(XAttnParams)]),
+    "naf_xattn_bwd_f32": (C.c_int, [C.POINTER(XAttnBwdParams), _fp]),
+    "naf_rope_kpool_bwd_f32": (C.c_int, [C.POINTER(KPoolBwdParams), _fp]),
     "naf_concat_bias_nhwc_f32": (C.c_int, [_fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int64, _fp]),
     "naf_gn_stats_f32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int64, C.c_int, C.c_int, _fp]),
     "naf_gn_silu_apply_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -208,6 +208,43 @@ int naf_rope_kpool_f32(const naf_kpool_params* pp, void* stream) {
   return launch_rope_kpool(p, static_cast<cudaStream_t>(stream));
 }
 
+int naf_xattn_bwd_f32(const naf_xattn_bwd_params* pp, void* stream) {
+  NAF_REQUIRE(pp, NAF_ERR_NULL, "xattn_bwd: NULL params");
+  const naf_xattn_bwd_params& p = *pp;
+  NAF_REQUIRE(p.q && p.k && p.v && p.dout && p.dq && p.dk && p.dv, NAF_ERR_NULL,
+              "xattn_bwd: q, k, v, dout, dq, dk and dv must be non-NULL");
+  // the forward's own validation, on the forward view of these parameters
+  naf_xattn_params f;
+  memset(&f, 0, sizeof(f));
+  f.q = p.q; f.k = p.k; f.v = p.v; f.out = p.dq;
+  f.row_tap = p.row_tap; f.col_tap = p.col_tap;
+  f.cos_y = p.cos_y; f.sin_y = p.sin_y; f.cos_x = p.cos_x; f.sin_x = p.sin_x;
+  f.B = p.B; f.D = p.D; f.C = p.C; f.heads = p.heads; f.Ho = p.Ho; f.Wo = p.Wo; f.h = p.h; f.w = p.w; f.K = p.K;
+  f.scale = p.scale;
+  f.q_stride_b = p.q_stride_b; f.q_stride_y = p.q_stride_y; f.q_stride_x = p.q_stride_x;
+  f.rep_y = p.rep_y; f.rep_x = p.rep_x;
+  int rc = validate_xattn(f);
+  if (rc != NAF_OK) return rc;
+  NAF_REQUIRE(p.algo == NAF_ALGO_AUTO || p.algo == NAF_ALGO_GENERIC || p.algo == NAF_ALGO_CELL_SIMT, NAF_ERR_UNSUPPORTED,
+              "xattn_bwd: algo %d (auto, generic or cell_simt)", p.algo);
+  return launch_xattn_bwd(p, static_cast<cudaStream_t>(stream));
+}
+
+int naf_rope_kpool_bwd_f32(const naf_kpool_bwd_params* pp, void* stream) {
+  NAF_REQUIRE(pp, NAF_ERR_NULL, "rope_kpool_bwd: NULL params");
+  const naf_kpool_bwd_params& p = *pp;
+  NAF_REQUIRE(p.dx && (p.dq || p.dk), NAF_ERR_NULL, "rope_kpool_bwd: dx and one of dq / dk required");
+  NAF_REQUIRE(p.B > 0 && p.D > 0 && p.Ho > 0 && p.Wo > 0 && p.D % 2 == 0, NAF_ERR_BAD_SHAPE,
+              "rope_kpool_bwd: sizes must be positive, D even");
+  NAF_REQUIRE(!p.dk || (p.h > 0 && p.w > 0), NAF_ERR_BAD_SHAPE, "rope_kpool_bwd: bad pooled size");
+  const int nrope = (p.cos_y != nullptr) + (p.sin_y != nullptr) + (p.cos_x != nullptr) + (p.sin_x != nullptr);
+  NAF_REQUIRE(nrope == 0 || nrope == 4, NAF_ERR_NULL, "rope_kpool_bwd: rope tables must be all given or all NULL");
+  if (nrope == 4)
+    NAF_REQUIRE(p.rope_heads > 0 && p.D % (4 * p.rope_heads) == 0, NAF_ERR_BAD_SHAPE,
+                "rope_kpool_bwd: embed_dim %% (4*num_heads) must be 0");
+  return launch_rope_kpool_bwd(p, static_cast<cudaStream_t>(stream));
+}
+
 int naf_xattn_select_algo(const naf_xattn_params* pp) {
   if (!pp) return -fail(NAF_ERR_NULL, "xattn: NULL params");
   int rc = validate_xattn(*pp);

@@ -136,6 +136,8 @@ int launch_pack_nhwc(const float* src, float* dst, int B, int C, int H, int W, i
                      cudaStream_t st);
 int launch_rope_kpool(const naf_kpool_params& p, cudaStream_t st);
 int launch_xattn_generic(const naf_xattn_params& p, cudaStream_t st);
+int launch_xattn_bwd(const naf_xattn_bwd_params& p, cudaStream_t st);
+int launch_rope_kpool_bwd(const naf_kpool_bwd_params& p, cudaStream_t st);
 bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_simt(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why);

@@ -47,7 +47,14 @@ class CrossAttention(nn.Module):
         hq, wq = q.shape[-2] * int(rep[0]), q.shape[-1] * int(rep[1])
         hk, wk = k.shape[-2:]
         self.dilation = (hq // hk, wq // wk)
+        out_dtype = autocast_out_dtype() if out_dtype is None else out_dtype
+        if (torch.is_grad_enabled() and any(t.requires_grad for t in (q, k, v)) and rope_tables is None
+                and tuple(rep) == (1, 1)):
+            # differentiable like the reference's NATTEN calls (train.py:136): forward = the same kernels
+            from ..autograd import XAttnFn
+            return XAttnFn.apply(q, k, v, self.num_heads, self._square_kernel(), self.scale, self.algo,
+                                 out_dtype, bool(return_weights))
         res = ops.xattn(q, k, v, self.num_heads, self._square_kernel(), scale=self.scale,
                         rope_tables=rope_tables, return_scores=return_weights, algo=self.algo, rep=rep,
-                        out_dtype=autocast_out_dtype() if out_dtype is None else out_dtype)
+                        out_dtype=out_dtype)
         return res

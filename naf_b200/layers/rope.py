@@ -6,9 +6,13 @@ The rotation itself runs in `naf_rope_kpool_f32`; inside `NAF.forward` it is fus
 attention kernel rotates q on the fly and the key pre-pass rotates while it pools), so this
 module's `forward` is only used when somebody calls RoPE on its own.
 
-Inference scope: the train-time coordinate augmentations (`shift_coords`, `jitter_coords`,
-`rescale_coords`; src/layers/rope.py:108-124) are accepted and stored but calling the module in
-training mode with any of them set raises -- the forward-only tier does not implement them.
+Coordinates follow `create_coordinate` (src/layers/rope.py:84-126) operation for operation: the three
+normalisations ("separate", "min", "max") and the train-time augmentations (`shift_coords`,
+`jitter_coords`, `rescale_coords`: random draws made with the same torch calls, in the same order, on
+the same device as the reference, so a seeded run draws the same numbers).  Every one of them acts per
+axis, so the coordinates -- and the cos/sin tables -- stay factored into a row part and a column part.
+Like the reference (:159-161) the coordinates are cached per (H, W): they are re-drawn only when the map
+size changes, whatever the training flag says.
 """
 from __future__ import annotations
 
@@ -68,21 +72,42 @@ class RoPE(nn.Module):
             periods = torch.logspace(math.log10(self.min_period), math.log10(self.max_period), steps=n)
         self.periods.data = periods
 
-    # -- tables -----------------------------------------------------------------------------
-    def axis_tables(self, H: int, W: int):
-        """(cos_y, sin_y, cos_x, sin_x) for an (H, W) map, cached per shape/device."""
-        if self.normalize_coords != "separate":
-            if self.normalize_coords in ("min", "max"):
-                raise NotImplementedError(
-                    "naf_b200 RoPE implements normalize_coords='separate' (the only mode NAF uses)")
+    # -- coordinates and tables --------------------------------------------------------------
+    def axis_coords(self, H: int, W: int):
+        """(coords_y (H,), coords_x (W,)) in [-1, 1]: `create_coordinate` of the reference, per axis."""
+        dev, dt = self.periods.device, self.dtype
+        dd = {"device": dev, "dtype": dt}
+        if self.normalize_coords == "max":
+            den_h = den_w = max(H, W)
+        elif self.normalize_coords == "min":
+            den_h = den_w = min(H, W)
+        elif self.normalize_coords == "separate":
+            den_h, den_w = H, W
+        else:
             raise ValueError(f"Unknown normalize_coords: {self.normalize_coords}")
-        if self.training and any(v is not None for v in (self.shift_coords, self.jitter_coords, self.rescale_coords)):
-            raise NotImplementedError(
-                "naf_b200 is forward/inference only: RoPE coordinate augmentation is a training "
-                "feature; call .eval() first")
+        cy = 2.0 * (torch.arange(0.5, H, **dd) / den_h) - 1.0
+        cx = 2.0 * (torch.arange(0.5, W, **dd) / den_w) - 1.0
+        if self.training and self.shift_coords is not None:
+            shift_hw = torch.empty(2, **dd).uniform_(-self.shift_coords, self.shift_coords)
+            cy, cx = cy + shift_hw[0], cx + shift_hw[1]
+        if self.training and self.jitter_coords is not None:
+            jitter_max = math.log(self.jitter_coords)
+            jitter_hw = torch.empty(2, **dd).uniform_(-jitter_max, jitter_max).exp()
+            cy, cx = cy * jitter_hw[0], cx * jitter_hw[1]
+        if self.training and self.rescale_coords is not None:
+            rescale_max = math.log(self.rescale_coords)
+            rescale_hw = torch.empty(1, **dd).uniform_(-rescale_max, rescale_max).exp()
+            cy, cx = cy * rescale_hw, cx * rescale_hw
+        return cy, cx
+
+    def axis_tables(self, H: int, W: int):
+        """(cos_y, sin_y, cos_x, sin_x) for an (H, W) map, cached per shape / device / periods (the
+        reference caches its coordinates per (H, W) too, src/layers/rope.py:159-161)."""
         key = (H, W, self.periods.device, self.periods.data_ptr(), self.periods._version)
         if key != self._table_key:
-            self._tables = ops.rope_axis_tables(H, W, self.periods.to(torch.float32))
+            cy, cx = self.axis_coords(H, W)
+            self._tables = ops.rope_tables_from_coords(cy.to(torch.float32), cx.to(torch.float32),
+                                                       self.periods.to(torch.float32))
             self._table_key = key
         return self._tables
 
@@ -102,7 +127,12 @@ class RoPE(nn.Module):
         B, D, H, W = x.shape
         if D != self.D_head * self.num_heads:
             raise ValueError(f"expected {self.D_head * self.num_heads} channels, got {D}")
-        _, q = ops.rope_kpool(x, self.axis_tables(H, W), self.num_heads, pooled_hw=None, want_q=True)
+        tables = self.axis_tables(H, W)
+        if torch.is_grad_enabled() and x.requires_grad:
+            from ..autograd import RoPEFn
+            q = RoPEFn.apply(x, tables, self.num_heads)
+        else:
+            _, q = ops.rope_kpool(x, tables, self.num_heads, pooled_hw=None, want_q=True)
         if layout == "spatial":
             return q
         if layout == "flatten":

@@ -116,6 +116,9 @@ class KeyEncoder(nn.Module):
     """K = block mean of the rotated guidance map at the feature resolution."""
 
     def forward(self, x, features):
+        if torch.is_grad_enabled() and x.requires_grad:
+            from ..autograd import KeyPoolFn
+            return KeyPoolFn.apply(x, tuple(features.shape[-2:]))
         k, _ = ops.rope_kpool(x, None, 1, pooled_hw=features.shape[-2:], want_q=False)
         return k
 
@@ -134,23 +137,42 @@ class NAF(nn.Module):
 
     def upsample_from_guidance(self, x, features, return_weights=False, rep=(1, 1), out_dtype=None):
         """The hot path proper: pooled un-rotated guidance x (B,D,Ho/ry,Wo/rx) + features
-        (B,C,h,w) -> (B,C,Ho,Wo).  Two kernel launches (+ one tiny packing launch for V)."""
+        (B,C,h,w) -> (B,C,Ho,Wo).  Two kernel launches (+ one tiny packing launch for V).
+        Differentiable w.r.t. x and features when grad mode is on (naf_b200/autograd.py)."""
         rope = self.image_encoder.rope
         Ho, Wo = x.shape[-2] * rep[0], x.shape[-1] * rep[1]
         tables = rope.axis_tables(Ho, Wo)
         D = x.shape[1]
-        x = ops.as_pixel_major(x)  # once, shared by both kernels
         fused = rope.D_head == D // self.upsampler.num_heads
         h, w = features.shape[-2:]
         ry, rx = int(rep[0]), int(rep[1])
+        # Key pooling over replicated guidance: every source pixel stands for an ry x rx block
+        # whose rotations differ only through the angles, and the rotation is linear, so the
+        # block mean of RoPE(x) is x rotated by the block-MEAN cos/sin.  Pool the source map
+        # with mean tables: 1/(ry*rx) of the work, identical result up to summation order.
+        pool_tables = None
         if fused and (ry > 1 or rx > 1) and Ho % h == 0 and Wo % w == 0 and (Ho // h) % ry == 0 \
                 and (Wo // w) % rx == 0:
-            # Key pooling over replicated guidance: every source pixel stands for an ry x rx block
-            # whose rotations differ only through the angles, and the rotation is linear, so the
-            # block mean of RoPE(x) is x rotated by the block-MEAN cos/sin.  Pool the source map
-            # with mean tables: 1/(ry*rx) of the work, identical result up to summation order.
-            k, q = ops.rope_kpool(x, rope.mean_axis_tables(Ho, Wo, ry, rx), rope.num_heads,
-                                  pooled_hw=(h, w), want_q=False)
+            pool_tables = rope.mean_axis_tables(Ho, Wo, ry, rx)
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or features.requires_grad)
+        if needs_grad:
+            if return_weights:
+                raise NotImplementedError("naf_b200: return_weights=True is an inference feature (no gradient "
+                                          "flows through the returned scores); call it under torch.no_grad()")
+            if fused:
+                from ..autograd import NAFUpsampleFn
+                return NAFUpsampleFn.apply(x.float(), features, tables, pool_tables, rope.num_heads,
+                                           self.upsampler.num_heads, self.upsampler._square_kernel(),
+                                           self.upsampler.scale, self.upsampler.algo, (ry, rx), out_dtype)
+            # rope heads != attention heads: compose the differentiable operators on the materialised map
+            if (ry, rx) != (1, 1):
+                x = x.repeat_interleave(ry, 2).repeat_interleave(rx, 3)
+            q = rope(x.float())
+            k = self.key_encoder(q, features)
+            return self.upsampler(q, k, features, out_dtype=out_dtype)
+        x = ops.as_pixel_major(x)  # once, shared by both kernels
+        if pool_tables is not None:
+            k, q = ops.rope_kpool(x, pool_tables, rope.num_heads, pooled_hw=(h, w), want_q=False)
         else:
             k, q = ops.rope_kpool(x, tables, rope.num_heads, pooled_hw=(h, w), want_q=not fused, rep=rep)
         if fused:
@@ -160,16 +182,27 @@ class NAF(nn.Module):
 
     def forward(self, image, features, output_size, return_weights=False, *args, out_dtype=None, **kwargs):
         """`out_dtype`: None = what the reference returns in this context (bf16 under bf16 autocast,
-        else fp32); torch.float32 / torch.bfloat16 to choose.  All arithmetic is fp32 either way."""
-        if torch.is_grad_enabled() and (features.requires_grad or image.requires_grad or
-                                        any(p.requires_grad for p in self.parameters())):
-            if torch.is_grad_enabled() and self.training:
-                raise RuntimeError("naf_b200.NAF is forward-only: use torch.no_grad() and .eval()")
+        else fp32); torch.float32 / torch.bfloat16 to choose.  All arithmetic is fp32 either way.
+
+        With grad mode on and anything that requires grad (the parameters in a training loop,
+        train.py:127-136; the features or the image when a backbone or a probe is trained through a
+        frozen NAF) the call is differentiable like the reference's: the conv encoder runs as plain torch
+        modules under autograd (cuDNN), the attention path through `naf_b200.autograd.NAFUpsampleFn`
+        (our forward AND backward kernels).  Otherwise: the inference path, all on our kernels."""
+        from ..layers.attentions import autocast_out_dtype
+        if out_dtype is None:
+            out_dtype = autocast_out_dtype()
+        needs_grad = torch.is_grad_enabled() and (features.requires_grad or image.requires_grad or
+                                                  any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            enc = self.image_encoder
+            Ho, Wo = int(output_size[0]), int(output_size[1])
+            x = enc.forward_encoder(enc._capped(image, Ho, Wo), (Ho, Wo))     # torch modules, autograd
+            with torch.autocast("cuda", enabled=False):
+                return self.upsample_from_guidance(x.float(), features, return_weights=return_weights,
+                                                   out_dtype=out_dtype)
         with torch.no_grad():
             x, rep = self.image_encoder.guidance_source(image, output_size)
-            if out_dtype is None:
-                from ..layers.attentions import autocast_out_dtype
-                out_dtype = autocast_out_dtype()
             with torch.autocast("cuda", enabled=False):
                 return self.upsample_from_guidance(x.float(), features, return_weights=return_weights, rep=rep,
                                                    out_dtype=out_dtype)

@@ -43,8 +43,9 @@ def _require_cuda(*tensors: torch.Tensor) -> torch.device:
 def _no_grad_guard(*tensors: torch.Tensor) -> None:
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
         raise RuntimeError(
-            "naf_b200 implements the forward pass only: call it under torch.no_grad() / "
-            "torch.inference_mode(), or detach the inputs")
+            "naf_b200.ops functions are the forward pass only: call them under torch.no_grad() / "
+            "torch.inference_mode(), detach the inputs, or go through the differentiable modules "
+            "(naf_b200.NAF / CrossAttention / RoPE, naf_b200.autograd)")
 
 
 def _stream(dev: torch.device) -> C.c_void_p:
@@ -128,19 +129,22 @@ def as_pixel_major(t: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------- rope tables
-def rope_axis_tables(H: int, W: int, periods: torch.Tensor):
-    """Per-axis cos/sin tables (cos_y, sin_y: (H,P); cos_x, sin_x: (W,P)), P = len(periods).
-
-    Same torch ops, in the same order, as the reference's RoPE (src/layers/rope.py:99-105 for
-    the "separate" coordinates, :139-146 for the angles) so the table entries are bit-identical
-    to the entries of its (H*W, D_head) cos/sin tensors on the same device."""
-    dev, dt = periods.device, periods.dtype
-    cy = 2.0 * (torch.arange(0.5, H, device=dev, dtype=dt) / H) - 1.0
-    cx = 2.0 * (torch.arange(0.5, W, device=dev, dtype=dt) / W) - 1.0
+def rope_tables_from_coords(cy: torch.Tensor, cx: torch.Tensor, periods: torch.Tensor):
+    """Per-axis cos/sin tables (cos_y, sin_y: (H,P); cos_x, sin_x: (W,P)), P = len(periods), from the
+    per-axis coordinates.  Same torch ops as the reference's `RoPE.rotate` (src/layers/rope.py:139-146)
+    so the entries are bit-identical to those of its (H*W, D_head) cos/sin tensors on the same device."""
     ang_y = 2 * math.pi * cy[:, None] / periods[None, :]
     ang_x = 2 * math.pi * cx[:, None] / periods[None, :]
     return (torch.cos(ang_y).contiguous(), torch.sin(ang_y).contiguous(),
             torch.cos(ang_x).contiguous(), torch.sin(ang_x).contiguous())
+
+
+def rope_axis_tables(H: int, W: int, periods: torch.Tensor):
+    """Tables for the default ("separate", eval) coordinates (src/layers/rope.py:99-105)."""
+    dev, dt = periods.device, periods.dtype
+    cy = 2.0 * (torch.arange(0.5, H, device=dev, dtype=dt) / H) - 1.0
+    cx = 2.0 * (torch.arange(0.5, W, device=dev, dtype=dt) / W) - 1.0
+    return rope_tables_from_coords(cy, cx, periods)
 
 
 # -------------------------------------------------------------------------- rope + key pooling
@@ -275,6 +279,85 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_
     _launch_xattn(p, dev)
     res = out.permute(0, 3, 1, 2)
     return (res, scores) if return_scores else res
+
+
+# ----------------------------------------------------------------------------------- backward
+def _contig_pixel_major(t: torch.Tensor) -> torch.Tensor:
+    """NCHW-shaped fp32 view whose (B,H,W,C) storage is fully contiguous."""
+    t = as_pixel_major(t)
+    if not t.permute(0, 2, 3, 1).is_contiguous():
+        t = pack_nhwc(t).permute(0, 3, 1, 2)
+    return t
+
+
+def xattn_bwd(q, k, v, dout, heads: int, kernel_size: int, scale: Optional[float] = None, rope_tables=None,
+              algo: int = _lib.ALGO_AUTO, rep=(1, 1)):
+    """Gradients of `xattn` (naf_xattn_bwd_f32).  q, k, v, rope_tables, rep, scale as given to the
+    forward; dout (B,C,Ho,Wo) is dL/dout.  Returns (dq, dk, dv) as NCHW-shaped pixel-major views:
+    dq (B,D,Ho,Wo) is the gradient w.r.t. the ROTATED queries (w.r.t. q itself without rope tables),
+    dk (B,D,h,w), dv (B,C,h,w)."""
+    dev = _require_cuda(q, k, v, dout)
+    B, D, Ho, Wo = q.shape
+    Ho, Wo = Ho * int(rep[0]), Wo * int(rep[1])
+    _, Cn, h, w = v.shape
+    K = int(kernel_size)
+    if tuple(dout.shape) != (B, Cn, Ho, Wo):
+        raise ValueError(f"dout{tuple(dout.shape)} does not match the output shape {(B, Cn, Ho, Wo)}")
+    if scale is None:
+        scale = (D // heads) ** -0.5
+    tap_tabs = device_tap_tables(Ho, Wo, h, w, K, dev)
+    q = as_pixel_major(q.detach())
+    k = _contig_pixel_major(k.detach())
+    v = _contig_pixel_major(v.detach())
+    dout = _contig_pixel_major(dout.detach())
+    dq = torch.empty((B, Ho, Wo, D), device=dev, dtype=torch.float32)
+    dk = torch.empty((B, h, w, D), device=dev, dtype=torch.float32)
+    dv = torch.empty((B, h, w, Cn), device=dev, dtype=torch.float32)
+    p = _lib.XAttnBwdParams()
+    p.q, p.k, p.v, p.dout, p.dq, p.dk, p.dv = (_ptr(t) for t in (q, k, v, dout, dq, dk, dv))
+    p.row_tap, p.col_tap = _ptr(tap_tabs[0]), _ptr(tap_tabs[1])
+    if rope_tables is not None:
+        p.cos_y, p.sin_y, p.cos_x, p.sin_x = (_ptr(t) for t in rope_tables)
+    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
+    p.scale = float(scale)
+    p.q_stride_b, _, p.q_stride_y, p.q_stride_x = q.stride()
+    p.algo = int(algo)
+    p.rep_y, p.rep_x = int(rep[0]), int(rep[1])
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_xattn_bwd_f32(C.byref(p), _stream(dev))
+    _lib.check(rc, "naf_xattn_bwd_f32")
+    return dq.permute(0, 3, 1, 2), dk.permute(0, 3, 1, 2), dv.permute(0, 3, 1, 2)
+
+
+def rope_kpool_bwd(dq, dk, tables, rope_heads: int, inplace: bool = False):
+    """Gradient of `rope_kpool` w.r.t. its input x (naf_rope_kpool_bwd_f32): dq (B,D,Ho,Wo) is the
+    gradient w.r.t. the rotated map (or None), dk (B,D,h,w) w.r.t. the pooled keys (or None);
+    tables as in the forward (None: no rotation).  Returns dx (B,D,Ho,Wo), pixel-major view."""
+    dev = _require_cuda(dq, dk)
+    if dq is None and dk is None:
+        raise ValueError("rope_kpool_bwd: nothing to propagate")
+    if dq is not None:
+        dq = _contig_pixel_major(dq.detach())
+        B, D, Ho, Wo = dq.shape
+    if dk is not None:
+        dk = _contig_pixel_major(dk.detach())
+    if dq is None:
+        if tables is None:
+            raise ValueError("rope_kpool_bwd: the map size is unknown without dq or tables")
+        B, D = dk.shape[:2]
+        Ho, Wo = tables[0].shape[0], tables[2].shape[0]
+    h, w = (dk.shape[-2], dk.shape[-1]) if dk is not None else (0, 0)
+    dx = dq.permute(0, 2, 3, 1) if (inplace and dq is not None) else torch.empty((B, Ho, Wo, D), device=dev, dtype=torch.float32)
+    p = _lib.KPoolBwdParams()
+    p.dq, p.dk, p.dx = _ptr(dq), _ptr(dk), _ptr(dx)
+    if tables is not None:
+        p.cos_y, p.sin_y, p.cos_x, p.sin_x = (_ptr(t) for t in tables)
+    p.B, p.D, p.Ho, p.Wo, p.h, p.w = B, D, Ho, Wo, h, w
+    p.rope_heads = int(rope_heads)
+    with torch.cuda.device(dev):
+        rc = _lib.load().naf_rope_kpool_bwd_f32(C.byref(p), _stream(dev))
+    _lib.check(rc, "naf_rope_kpool_bwd_f32")
+    return dx.permute(0, 3, 1, 2)
 
 
 def select_algo(q_shape, v_shape, heads: int, kernel_size: int, rope_on_the_fly: bool = True,

@@ -200,3 +200,28 @@ def image_encoder_resolution(Hi: int, Wi: int, Ho: int, Wo: int) -> tuple[int, i
     if Hi > 4 * Ho or Wi > 4 * Wo:
         return min(Hi, 4 * Ho, 4 * Wo), min(Wi, 4 * Wo, 4 * Ho)
     return Hi, Wi
+
+
+# ------------------------------------------------------------------------------ backward
+def cross_attention_grads(q, k, v, dout, num_heads: int, kernel_size, dtype=torch.float64):
+    """Gradients (dq, dk, dv) of sum(cross_attention(q, k, v) * dout), by torch autograd through this
+    file's own forward restatement (evaluated in `dtype`, fp64 by default: the gradcheck reference of
+    the CUDA backward).  Follows what autograd does to the reference's legacy_attention
+    (/root/reference/src/layers/attentions.py:16-29): softmax backward on the scaled logits, dV as the
+    scatter-add of P^T dOut over the shared windows, dK likewise from dS^T Q."""
+    qd, kd, vd = (t.detach().to(dtype).requires_grad_(True) for t in (q, k, v))
+    out = cross_attention(qd, kd, vd, num_heads, kernel_size)
+    out.backward(dout.to(dtype))
+    return qd.grad, kd.grad, vd.grad
+
+
+def naf_forward_grads(x_pooled, features, dout, heads_attn: int, heads_rope: int, kernel_size,
+                      rope_base: float = 100.0, dtype=torch.float64):
+    """Gradients (dx, dfeatures) of sum(naf_forward(x, features) * dout): the hot path downstream of the
+    conv encoder -- dQ through the transposed rotation, dK through the key pooling
+    (/root/reference/src/model/naf.py:63-69,108: K is pooled from the ROTATED map, so every pixel also
+    receives 1/|bin| of its bins' dK), dV scatter-add."""
+    xd, fd = (t.detach().to(dtype).requires_grad_(True) for t in (x_pooled, features))
+    out = naf_forward(xd, fd, heads_attn, heads_rope, kernel_size, rope_base)
+    out.backward(dout.to(dtype))
+    return xd.grad, fd.grad

@@ -64,3 +64,26 @@ def default_case(name):
 def default_state():
     d = np.load(os.path.join(GOLDEN, "naf256_k7_state.npz"))
     return {k: torch.from_numpy(d[k]) for k in d.files}
+
+
+# ---- gradient fixtures (oracle/gen_golden_bwd.py: autograd through the unmodified reference) -------
+def bwd_attention_case(name):
+    d = load(name)
+    seed = int(d["seed"])
+    return dict(q=seeded_normal(seed, d["q_shape"]) * float(d["gain"]), k=seeded_normal(seed + 1, d["k_shape"]),
+                v=seeded_normal(seed + 2, d["v_shape"]),
+                dout=seeded_normal(seed + 3, (d["q_shape"][0], d["v_shape"][1], d["q_shape"][2], d["q_shape"][3])),
+                out=torch.from_numpy(d["out"]), dq=torch.from_numpy(d["dq"]), dk=torch.from_numpy(d["dk"]),
+                dv=torch.from_numpy(d["dv"]), heads=int(d["heads"]), K=int(d["kernel_size"]))
+
+
+def bwd_module_case(name):
+    d = load(name)
+    seed = int(d["seed"])
+    Ho, Wo = (int(x) for x in d["output_size"])
+    feats_shape = d["features_shape"]
+    grads = {k[len("grad__"):]: torch.from_numpy(d[k]) for k in d if k.startswith("grad__")}
+    return dict(image=seeded_normal(seed, d["image_shape"]), features=seeded_normal(seed + 1, feats_shape),
+                dout=seeded_normal(seed + 2, (1, int(feats_shape[1]), Ho, Wo)), out=torch.from_numpy(d["out"]),
+                dimage=torch.from_numpy(d["dimage"]), dfeatures=torch.from_numpy(d["dfeatures"]),
+                output_size=(Ho, Wo), grads=grads)

@@ -17,7 +17,7 @@ from naf_b200.layers import encoder
 
 pytestmark = pytest.mark.gpu
 
-TOL = {3: 2e-5, 1: 4e-3, -1: 4e-3, -3: 4e-3}   # -1, -3: alternative 1-pass kernels kept for A/B timing
+TOL = {3: 2e-5, 1: 4e-3}
 
 
 def dev():
@@ -67,7 +67,7 @@ def test_stem_conv_and_partials(ks, shape, tc):
     assert (part.cpu().double().view(B, tiles, 8, 2) - wp).abs().max().item() <= 1e-5 * max(1.0, wp.abs().max().item())
 
 
-@pytest.mark.parametrize("passes", [3, 1, -1, -3])
+@pytest.mark.parametrize("passes", [3, 1])
 @pytest.mark.parametrize("ks", [1, 3])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_gn_silu_conv_kernel(ks, passes, shape):
@@ -114,7 +114,7 @@ def test_gn_silu_conv_kernel(ks, passes, shape):
     assert (gp - wp).abs().max().item() <= 1e-5 * max(1.0, wp.abs().max().item())
 
 
-@pytest.mark.parametrize("passes", [3, 1, -1, -3])
+@pytest.mark.parametrize("passes", [3, 1])
 @pytest.mark.parametrize("ks", [1, 3])
 def test_whole_branch_matches_torch_modules(ks, passes):
     torch.manual_seed(3)

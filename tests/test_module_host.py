@@ -81,11 +81,21 @@ def test_constructor_errors_match_reference():
     assert naf_b200.CrossAttention(256, 4, (9, 9)).scale == 0.125
 
 
-def test_training_mode_augmentation_is_refused():
+def test_training_mode_augmentation_and_coordinate_cache():
+    """Train mode draws the rescale augmentation (reference src/layers/rope.py:119-124); like the
+    reference (:159-161) the coordinates are cached per map size, so the same size re-uses them."""
+    import torch
     rope = naf_b200.RoPE(64, num_heads=4, rescale_coords=2.0).train()
-    with pytest.raises(NotImplementedError):
-        rope.axis_tables(4, 4)
-    rope.eval().axis_tables(4, 4)
+    torch.manual_seed(5)
+    a = rope.axis_tables(4, 6)
+    assert rope.axis_tables(4, 6) is a                      # cached per (H, W)
+    plain = naf_b200.RoPE(64, num_heads=4, rescale_coords=2.0).eval().axis_tables(4, 6)
+    assert not torch.equal(a[0], plain[0])                  # augmented coordinates differ from eval ones
+    with pytest.raises(ValueError):
+        naf_b200.RoPE(64, num_heads=4, normalize_coords="diagonal").axis_tables(4, 4)
+    for mode in ("min", "max"):
+        t = naf_b200.RoPE(64, num_heads=4, normalize_coords=mode).eval().axis_tables(4, 6)
+        assert t[0].shape == (4, 4) and t[2].shape == (6, 4)
 
 
 def test_default_width_encoder_on_cpu_plus_oracle_matches_reference_golden():

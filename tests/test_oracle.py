@@ -172,3 +172,38 @@ def test_per_pixel_rope_equals_the_map_rotation():
     got = O.rope_rotate_pixels(torch.stack([x[0, :, y, xx] for y, xx in zip(ys, xs)]), ys, xs, 9, 13, 4, per)
     want = torch.stack([full[0, :, y, xx] for y, xx in zip(ys, xs)])
     assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize("mode", ["separate", "min", "max"])
+@pytest.mark.parametrize("train", [False, True])
+def test_rope_coordinates_match_live_reference(mode, train):
+    """naf_b200.RoPE.axis_coords (pure torch, per axis) == the reference's create_coordinate
+    (src/layers/rope.py:84-126) for the three normalisations and, with the same seed, for the train-time
+    shift / jitter / rescale augmentations (same torch RNG calls in the same order)."""
+    if not reference_runner.available():
+        pytest.skip("reference tree not available")
+    import naf_b200
+    ns = reference_runner.load()
+    kw = dict(num_heads=2, base=100.0, normalize_coords=mode, shift_coords=0.1 if train else None,
+              jitter_coords=1.5 if train else None, rescale_coords=2.0)
+    ref = ns.RoPE(64, **kw)
+    ours = naf_b200.RoPE(64, **kw)
+    ref.train(train)
+    ours.train(train)
+    H, W = 7, 11
+    torch.manual_seed(123)
+    want = ref.create_coordinate(H=H, W=W).view(H, W, 2)
+    torch.manual_seed(123)
+    cy, cx = ours.axis_coords(H, W)
+    assert torch.equal(want[:, 0, 0], cy) and torch.equal(want[0, :, 1], cx)
+    assert torch.equal(want[:, :, 0], cy[:, None].expand(H, W)) and torch.equal(want[:, :, 1], cx[None, :].expand(H, W))
+
+
+@pytest.mark.parametrize("name", G.names("bwd_xattn_"))
+def test_oracle_gradients_match_reference_golden(name):
+    """The fp64 autograd oracle used as the gradcheck reference of the CUDA backward == gradients of the
+    unmodified reference modules (fp32) on the committed fixtures."""
+    c = G.bwd_attention_case(name)
+    dq, dk, dv = O.cross_attention_grads(c["q"], c["k"], c["v"], c["dout"], c["heads"], c["K"])
+    for got, want in ((dq, c["dq"]), (dk, c["dk"]), (dv, c["dv"])):
+        assert (got.float() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
