@@ -279,7 +279,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tcws"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tcws", "cell_tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-d2h", default="full", choices=["full", "sample", "both"],
                     help="what the e2e step reads back: the whole result (default; `e2e`), one value per "

@@ -146,16 +146,25 @@ typedef struct naf_xattn_params {
   int32_t out_dtype;     /* NAF_DTYPE_F32 (0) or NAF_DTYPE_BF16 (1): element type of `out` only.  bf16 is what the
                             reference returns under torch.autocast(bfloat16) (train.py:120, denoising.py:209);
                             arithmetic stays fp32, the result is rounded to nearest-even on the final store.
-                            Served by the pipelined tensor-core kernel and the generic kernel. */
+                            Served by the pipelined tensor-core kernels and the generic kernel. */
+  void* workspace;       /* scratch the TMA kernel keeps its fp16 hi/lo K and V planes in (>= naf_xattn_workspace_bytes,
+                            any alignment; contents undefined before and after the call); NULL: AUTO skips that kernel */
+  int64_t workspace_bytes;
 } naf_xattn_params;
 
 enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1 };
 
 enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2,
        NAF_ALGO_CELL_TC = 3 /* removed in ABI v3 (non-pipelined tensor-core kernel); requests fail with NAF_ERR_UNSUPPORTED */,
-       NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline */ };
+       NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline, windows converted in the kernel */,
+       NAF_ALGO_CELL_TMA = 5  /* the same pipeline fed by tensor-map TMA: pre-split K / V planes, window boxes,
+                                  single-pass wide value heads, tensor stores (needs `workspace`) */ };
 
 NAF_API int naf_xattn_fwd_f32(const naf_xattn_params* p, void* stream);
+
+/* Bytes of `workspace` the fastest kernel for these parameters wants (0 if none does).  The C side never
+ * allocates: the caller passes device scratch of at least this size in naf_xattn_params.workspace. */
+NAF_API size_t naf_xattn_workspace_bytes(const naf_xattn_params* p);
 
 /* ------------------------------------------------------------------------------------------
  * Backward of the cross-scale neighbourhood attention.

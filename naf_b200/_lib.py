@@ -15,9 +15,10 @@ LIB_PATH = os.environ.get("NAF_B200_LIB") or os.path.join(_HERE, "csrc", "libnaf
 ABI_VERSION = 3
 
 NAF_OK, NAF_ERR_BAD_SHAPE, NAF_ERR_UNSUPPORTED, NAF_ERR_WINDOW, NAF_ERR_ALIGNMENT, NAF_ERR_NULL, NAF_ERR_CUDA = range(7)
-ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS = range(5)
+ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS, ALGO_CELL_TMA = range(6)
 # (3 was the non-pipelined tensor-core kernel, removed in ABI v3; the value stays reserved)
-ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TCWS: "cell_tcws"}
+ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TCWS: "cell_tcws",
+              ALGO_CELL_TMA: "cell_tma"}
 
 _fp = C.c_void_p  # device pointers travel as integers
 
@@ -51,6 +52,7 @@ class XAttnParams(C.Structure):
         ("scale", C.c_float),
         ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
         ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32), ("out_dtype", C.c_int32),
+        ("workspace", _fp), ("workspace_bytes", C.c_int64),
     ]
 
     def __init__(self, *a, **kw):
@@ -103,6 +105,7 @@ EXPORTS = {
     "naf_rope_kpool_f32": (C.c_int, [C.POINTER(KPoolParams), _fp]),
     "naf_xattn_fwd_f32": (C.c_int, [C.POINTER(XAttnParams), _fp]),
     "naf_xattn_select_algo": (C.c_int, [C.POINTER(XAttnParams)]),
+    "naf_xattn_workspace_bytes": (C.c_size_t, [C.POINTER(XAttnParams)]),
     "naf_xattn_bwd_f32": (C.c_int, [C.POINTER(XAttnBwdParams), _fp]),
     "naf_rope_kpool_bwd_f32": (C.c_int, [C.POINTER(KPoolBwdParams), _fp]),
     "naf_concat_bias_nhwc_f32": (C.c_int, [_fp, _fp, C.c_int, _fp, _fp, C.c_int, _fp, C.c_int64, _fp]),

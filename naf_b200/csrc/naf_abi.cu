@@ -129,6 +129,10 @@ static int validate_xattn(const naf_xattn_params& p) {
 static int select_algo(const naf_xattn_params& p, bool explain) {
   const char* why = "";
   if (p.algo == NAF_ALGO_GENERIC) return NAF_ALGO_GENERIC;
+  if (p.algo == NAF_ALGO_CELL_TMA) {
+    if (xattn_cell_tma_supported(p, &why)) return NAF_ALGO_CELL_TMA;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: TMA tensor-core cell kernel unsupported: %s", why);
+  }
   if (p.algo == NAF_ALGO_CELL_TCWS) {
     if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
     return -fail(NAF_ERR_UNSUPPORTED, "xattn: pipelined tensor-core cell kernel unsupported: %s", why);
@@ -142,6 +146,7 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
   }
   if (p.algo != NAF_ALGO_AUTO) return -fail(NAF_ERR_UNSUPPORTED, "xattn: unknown algo %d", p.algo);
   (void)explain;
+  if (xattn_cell_tma_supported(p, &why)) return NAF_ALGO_CELL_TMA;
   if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
   if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
   return NAF_ALGO_GENERIC;
@@ -252,6 +257,18 @@ int naf_xattn_select_algo(const naf_xattn_params* pp) {
   return select_algo(*pp, true);
 }
 
+size_t naf_xattn_workspace_bytes(const naf_xattn_params* pp) {
+  if (!pp || validate_xattn(*pp) != NAF_OK) return 0;
+  // ask "would the TMA kernel take this if it had its workspace?"
+  naf_xattn_params q = *pp;
+  q.workspace = reinterpret_cast<void*>(uintptr_t(256));
+  q.workspace_bytes = INT64_MAX;
+  const char* why = "";
+  if ((q.algo == NAF_ALGO_AUTO || q.algo == NAF_ALGO_CELL_TMA) && xattn_cell_tma_supported(q, &why))
+    return xattn_cell_tma_workspace(q);
+  return 0;
+}
+
 int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
   NAF_REQUIRE(pp, NAF_ERR_NULL, "xattn: NULL params");
   const naf_xattn_params& p = *pp;
@@ -261,6 +278,8 @@ int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
   if (algo < 0) return -algo;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (algo) {
+    case NAF_ALGO_CELL_TMA:
+      return launch_xattn_cell_tma(p, st);
     case NAF_ALGO_CELL_TCWS:
       return launch_xattn_cell_tcws(p, st);
     case NAF_ALGO_CELL_SIMT:

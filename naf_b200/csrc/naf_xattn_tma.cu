@@ -1,0 +1,832 @@
+// Cell kernel, TMA edition: the warp-specialised tcgen05 / TMEM pipeline of naf_xattn_tcws.cu with every
+// bulk data movement except the per-pixel query loads handed to the tensor-map TMA engine.
+//
+//   * K / V windows.  A pre-pass (kv_planes_kernel) splits the low-resolution key and value maps ONCE into
+//     fp16 hi / lo "channel-group planes"  (B, 2, C/8, h, w, 8).  The K x K window of a (cell, head) item
+//     is then ONE cp.async.bulk.tensor.4d box per plane (UTMALDG): it lands in shared memory as
+//     [channel group][tap][16 B], which IS a valid SWIZZLE_NONE UMMA operand image --
+//         QK^T : K-major  B, LBO = K*K*16 (next channel group), SBO = 128 (next 8 taps)
+//         P V  : MN-major B, LBO = 128 (next 8 taps),           SBO = K*K*16 (next channel group)
+//     (tests/test_gpu_tma.py pins both against torch.matmul).  No thread converts or stores a window
+//     element any more (naf_xattn_tcws.cu re-converted every K / V element once per window holding it,
+//     49 or 121 times), and the window buffers shrink from TP-padded to exact K*K taps.
+//   * Wide value heads.  O is accumulated in NH column halves of DVH channels against ONE P
+//     (P stays in TMEM over the S columns): K = 11, dv = 256 (BASELINE config C3) runs in a single pass
+//     -- scores, softmax and the fp16 split of P are computed once per tile instead of once per value slab.
+//   * Output.  The epilogue stages normalised O in SWIZZLE_128B box images (conflict-free 16-byte
+//     st.shared) and ONE thread issues a handful of cp.async.bulk.tensor.4d stores per tile (UTMASTG:
+//     box = 32 channels x cell width x tile rows) instead of 256 per-thread bulk copies.
+//
+//   warps 0-7  "front": q half rows HBM -> registers (two tiles ahead), RoPE, fp16 hi/lo split, tcgen05.st;
+//                       softmax on S (tcgen05.ld), un-normalised P back over S, row sums to TMEM
+//   warps 8-15 "back" : drain O (tcgen05.ld), normalise, swizzled staging, tensor stores
+//   warp 16    "mma"  : one thread issues every tcgen05.mma:  QK(0) QK(1) PV(0,*) QK(2) PV(1,*) ...
+//   warp 17    "load" : one thread issues the window boxes of item i+1 while item i computes
+//
+// Tiles are whole pixel rows of the cell (th rows x rw pixels <= 128 TMEM lanes), so that a tile is a
+// rectangle of the output image.  Shapes this kernel does not take (cell width > 128 pixels, value dims
+// outside the table below) stay on naf_xattn_tcws.cu.
+//
+// Reference semantics: src/layers/attentions.py:16-29,53-75; RoPE src/layers/rope.py:137-153.
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "naf_common.cuh"
+#include "naf_tmap.cuh"
+#include "naf_umma.cuh"
+
+namespace naf {
+
+using namespace umma;
+
+namespace {
+
+constexpr int DQ = 64;
+constexpr int KC = DQ / 8;
+constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 64;
+constexpr int MMA_WARP = (NFRONT + NBACK) / 32, LOAD_WARP = MMA_WARP + 1;
+constexpr int kSmemLimit = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (static barriers extra)
+
+template <int TP>
+struct TmaWindowOf { static constexpr int K = TP == 16 ? 3 : TP == 32 ? 5 : TP == 64 ? 7 : TP == 96 ? 9 : 11; };
+
+constexpr int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// TP: padded taps; DVH: value channels per accumulator half; NH: halves; ROUNDS: staging rounds per half
+template <int TP, int DVH, int NH, int ROUNDS>
+struct TmaCfg {
+  static constexpr int K = TmaWindowOf<TP>::K, K2 = K * K;
+  static constexpr int DV = DVH * NH;
+  // one fp16 plane of a window: [channel group][tap][16 B]; the MMAs read TP >= K2 taps, i.e. up to 240 B
+  // past the last channel group: every plane is followed by >= 256 B that are zeroed once and never written
+  static constexpr int kKPlane = KC * K2 * 16;
+  static constexpr int kKStride = round_up(kKPlane + 256, 128);
+  static constexpr int kKWin = 2 * kKStride;                    // hi | lo
+  static constexpr int kVPlane = (DV / 8) * K2 * 16;
+  static constexpr int kVStride = round_up(kVPlane + 256, 128);
+  static constexpr int kVWin = 2 * kVStride;
+  static constexpr int kRoundCols = DVH / ROUNDS;               // output columns staged per round
+  static constexpr int kBox = 128 * 128;                        // one staging box image: 128 rows x 128 B
+  static constexpr int kStage = (kRoundCols / 32) * kBox;       // fp32: 32 channels per box (bf16: 64, half the boxes)
+  static constexpr int kMx = 2 * 2 * 128 * 4;                   // row-max exchange between the two row halves
+  static constexpr int NKB = 2;
+  static constexpr int kFixed = NKB * kKWin + kStage + kMx;
+  static constexpr int NVB = (kFixed + 2 * kVWin <= kSmemLimit) ? 2 : 1;
+  static constexpr int kSmemTotal = kFixed + NVB * kVWin;
+  static constexpr int kOffK = 0;
+  static constexpr int kOffV = NKB * kKWin;
+  static constexpr int kOffStage = round_up(kOffV + NVB * kVWin, 1024);
+  static constexpr int kOffMx = kOffStage + kStage;
+  static constexpr int kSmemBytes = kOffMx + kMx;
+  static constexpr int kQStages = (128 + 2 * TP + DVH + 8 <= 512) ? 2 : 1;
+  static constexpr int kTmemQ = 0;
+  static constexpr int kTmemS = 64 * kQStages;
+  static constexpr int kTmemO = kTmemS + 2 * TP;
+  static constexpr int kTmemL = kTmemO + DVH;
+  static constexpr int kTmemUsed = kTmemL + 8;
+  static constexpr bool kFits = kTmemUsed <= 512 && kSmemBytes <= kSmemLimit && (DVH % ROUNDS) == 0 &&
+                                (kRoundCols % 32) == 0 && DVH % 16 == 0 && DVH <= 256 && DV / 8 <= 256;
+};
+
+__device__ __forceinline__ uint64_t tm_pack2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void tm_unpack2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t tm_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+struct TmFastDiv {
+  uint32_t d, magic, shift;
+};
+struct TmDivs {
+  TmFastDiv ntiles, heads, w, h, rw, rep_y, rep_x;
+};
+__device__ __forceinline__ int tm_div(int n, const TmFastDiv& f) {
+  return f.magic == 0 ? (n >> f.shift) : int(__umulhi(uint32_t(n), f.magic) >> f.shift);
+}
+
+struct TmItem {
+  int b, ci, cj, head;
+};
+__device__ __forceinline__ TmItem tm_decode(int item, const TmDivs& dv) {
+  TmItem c;
+  int q = tm_div(item, dv.heads);
+  c.head = item - q * int(dv.heads.d);
+  item = q;
+  q = tm_div(item, dv.w);
+  c.cj = item - q * int(dv.w.d);
+  item = q;
+  q = tm_div(item, dv.h);
+  c.ci = item - q * int(dv.h.d);
+  c.b = q;
+  return c;
+}
+
+struct TmGeom {
+  int rh, rw;          // cell size in target pixels
+  int th;              // image rows per tile; tile_rows = th * rw <= 128
+  int ntiles;          // ceil(rh / th)
+  int th_last;         // rows of the last tile
+  int n_items;
+  int groups_k, groups_v;   // channel groups per (batch, plane) of the K / V plane tensors: D/8, C/8
+};
+
+}  // namespace
+
+// ---- pre-pass: fp32 (B,h,w,Cn) map -> fp16 hi / lo channel-group planes (B, 2, Cn/8, h, w, 8) ----------
+__global__ void __launch_bounds__(256)
+kv_planes_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int h, int w, int Cn) {
+  const int G = Cn / 8;
+  const int64_t total = int64_t(B) * G * h * w;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    // x fastest (coalesced 16-byte plane writes), then y, channel group, batch
+    const int x = int(i % w);
+    int64_t r = i / w;
+    const int y = int(r % h);
+    r /= h;
+    const int g = int(r % G);
+    const int b = int(r / G);
+    float v[8];
+    ldg8(src + ((int64_t(b) * h + y) * w + x) * Cn + g * 8, v);
+    uint4 hi, lo;
+    split2_f16(v[0], v[1], hi.x, lo.x);
+    split2_f16(v[2], v[3], hi.y, lo.y);
+    split2_f16(v[4], v[5], hi.z, lo.z);
+    split2_f16(v[6], v[7], hi.w, lo.w);
+    const int64_t plane = int64_t(h) * w;
+    dst[((int64_t(b) * 2 + 0) * G + g) * plane + int64_t(y) * w + x] = hi;
+    dst[((int64_t(b) * 2 + 1) * G + g) * plane + int64_t(y) * w + x] = lo;
+  }
+}
+
+// 18 warps x 112 registers = 64512 <= 65536 (ptxas settles for 96 under __launch_bounds__(576, 1) and spills
+// the 128-tap softmax rows)
+template <int TP, int DVH, int NH, int ROUNDS>
+__global__ void __maxnreg__(112)
+xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                      const __grid_constant__ CUtensorMap tmO2) {
+  using Cfg = TmaCfg<TP, DVH, NH, ROUNDS>;
+  constexpr int K = Cfg::K, K2 = Cfg::K2;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_o_full, bar_o_free;
+  __shared__ uint64_t bar_k_full[2], bar_k_free[2], bar_v_full[2], bar_v_free[2];
+  __shared__ uint32_t tmem_base_s;
+
+  uint8_t* const sK = smem + Cfg::kOffK;
+  uint8_t* const sV = smem + Cfg::kOffV;
+  uint8_t* const stage_out = smem + Cfg::kOffStage;
+  float* const mx = reinterpret_cast<float*>(smem + Cfg::kOffMx);   // [tile parity][half][row]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rh = gm.rh, rw = gm.rw;
+  const int npix = rh * rw;
+  const int ntiles = gm.ntiles;
+  const int tile_rows = gm.th * rw;
+  const int my_items = (gm.n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
+  auto item_of = [&](int it_seq) { return tm_decode(blockIdx.x + it_seq * gridDim.x, dv); };
+
+  if (warp == MMA_WARP) tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_q_full[s], NFRONT);
+      mbar_init(&bar_s_full[s], 1);
+      mbar_init(&bar_p_full[s], NFRONT);
+      mbar_init(&bar_k_full[s], 1);
+      mbar_init(&bar_k_free[s], 1);
+      mbar_init(&bar_v_full[s], 1);
+      mbar_init(&bar_v_free[s], 1);
+    }
+    mbar_init(&bar_o_full, 1);
+    mbar_init(&bar_o_free, NBACK);
+    fence_mbar_init();
+  }
+  // zero the tails the MMAs over-read behind every window plane (never written afterwards)
+  for (int i = tid; i < Cfg::NKB * 2 * (Cfg::kKStride - Cfg::kKPlane) / 16; i += NTHREADS) {
+    const int per = (Cfg::kKStride - Cfg::kKPlane) / 16;
+    const int pl = i / per, o = i - pl * per;
+    *reinterpret_cast<uint4*>(sK + pl * Cfg::kKStride + Cfg::kKPlane + o * 16) = make_uint4(0, 0, 0, 0);
+  }
+  for (int i = tid; i < Cfg::NVB * 2 * (Cfg::kVStride - Cfg::kVPlane) / 16; i += NTHREADS) {
+    const int per = (Cfg::kVStride - Cfg::kVPlane) / 16;
+    const int pl = i / per, o = i - pl * per;
+    *reinterpret_cast<uint4*>(sV + pl * Cfg::kVStride + Cfg::kVPlane + o * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const int total_tiles = my_items * ntiles;
+
+  if (warp < 8) {
+    // ======================================================================== FRONT
+    const int rowgrp = warp & 3, half = warp >> 2;
+    const int row = rowgrp * 32 + lane;
+    const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
+    constexpr int HALF = DQ / 2, P = DQ / 4, SC = TP / 2;
+    const bool rope = p.cos_y != nullptr;
+    const float qscale = p.scale * 1.4426950408889634f;
+
+    float qa[P], qb[P];
+    int q_y = 0, q_x = 0;
+
+    int f_g = 0;   // issue_q is called for g = 0, 1, 2, ... in order
+    auto issue_q = [&]() {
+      const int g = f_g++;
+      const int it_seq = tm_div(g, dv.ntiles), tile = g - it_seq * ntiles;
+      const TmItem it = item_of(it_seq);
+      int pi = tile * tile_rows + row;
+      const int lim = min(npix, (tile + 1) * tile_rows);
+      if (pi >= lim) pi = lim - 1;
+      const int py = tm_div(pi, dv.rw);
+      q_y = it.ci * rh + py;
+      q_x = it.cj * rw + (pi - py * rw);
+      const float* qp = p.q + int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
+                        int64_t(tm_div(q_y, dv.rep_y)) * p.q_stride_y + int64_t(tm_div(q_x, dv.rep_x)) * p.q_stride_x;
+      ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
+      ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
+      ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
+      ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+    };
+    // rotate + scale + split the prefetched q and write it to TMEM:
+    // columns [0,32) hi, [32,64) lo; two channels per 32-bit column
+    constexpr int QS = Cfg::kQStages;
+    auto stage_q = [&](int g) {   // g: the tile whose q is in the registers
+      if (rope) {
+        const float* ct = half == 0 ? p.cos_y + int64_t(q_y) * P : p.cos_x + int64_t(q_x) * P;
+        const float* st = half == 0 ? p.sin_y + int64_t(q_y) * P : p.sin_x + int64_t(q_x) * P;
+        float c[P], sn[P];
+        ldg8(ct, *reinterpret_cast<float(*)[8]>(&c[0]));
+        ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
+        ldg8(st, *reinterpret_cast<float(*)[8]>(&sn[0]));
+        ldg8(st + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+        const uint64_t qs2 = tm_pack2(qscale, qscale);
+#pragma unroll
+        for (int j = 0; j < P; j += 2) {
+          const uint64_t a2 = tm_pack2(qa[j], qa[j + 1]), b2 = tm_pack2(qb[j], qb[j + 1]);
+          const uint64_t c2 = tm_pack2(c[j], c[j + 1]), s2 = tm_pack2(sn[j], sn[j + 1]);
+          const uint64_t ra = tm_fma2(b2 ^ 0x8000000080000000ull, s2, tm_fma2(a2, c2, 0ull));
+          const uint64_t rb = tm_fma2(a2, s2, tm_fma2(b2, c2, 0ull));
+          tm_unpack2(tm_fma2(ra, qs2, 0ull), qa[j], qa[j + 1]);
+          tm_unpack2(tm_fma2(rb, qs2, 0ull), qb[j], qb[j + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+          qa[j] *= qscale;
+          qb[j] *= qscale;
+        }
+      }
+      const uint32_t tq = tmem + Cfg::kTmemQ + (QS == 2 ? (g & 1) * 64 : 0) + lane_off;
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split2_f16(qa[2 * j], qa[2 * j + 1], hi[j], lo[j]);
+      tmem_st8(tq + 8 * half, hi);
+      tmem_st8(tq + 32 + 8 * half, lo);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) split2_f16(qb[2 * j], qb[2 * j + 1], hi[j], lo[j]);
+      tmem_st8(tq + 16 + 8 * half, hi);
+      tmem_st8(tq + 48 + 8 * half, lo);
+      wait_st();
+      fence_before_sync();
+      mbar_arrive(&bar_q_full[QS == 2 ? (g & 1) : 0]);
+    };
+
+    if (total_tiles > 0) {
+      issue_q();
+      stage_q(0);
+      if (total_tiles > 1) issue_q();
+    }
+    for (int g = 0; g < total_tiles; ++g) {
+      const int s = g & 1;
+      if constexpr (QS == 2) {
+        if (g + 1 < total_tiles) {
+          stage_q(g + 1);
+          if (g + 2 < total_tiles) issue_q();
+        }
+      }
+      mbar_wait(&bar_s_full[s], (g >> 1) & 1);
+      fence_after_sync();
+      if constexpr (QS == 1) {
+        if (g + 1 < total_tiles) {
+          stage_q(g + 1);
+          if (g + 2 < total_tiles) issue_q();
+        }
+      }
+      const uint32_t ts = tmem + Cfg::kTmemS + s * TP + lane_off;
+      auto softmax_half = [&](auto half_c) {
+        constexpr int H = decltype(half_c)::value;
+        constexpr int base = H * SC;
+        constexpr int NV = K2 - base < 0 ? 0 : (K2 - base > SC ? SC : K2 - base);   // valid taps of this half
+        uint32_t mine[SC];
+        if constexpr (SC % 16 == 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 16) tmem_ld16(ts + base + c0, *reinterpret_cast<uint32_t(*)[16]>(&mine[c0]));
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(ts + base + c0, *reinterpret_cast<uint32_t(*)[8]>(&mine[c0]));
+        }
+        wait_ld();
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) m = fmaxf(m, __uint_as_float(mine[j]));
+        // the two halves of a row exchange their partial maxima through shared memory; the same named
+        // barrier orders the S reads of both halves before P overwrites the S columns
+        float* mslot = mx + (s * 2) * 128 + row;
+        mslot[H * 128] = m;
+        fence_before_sync();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        fence_after_sync();
+        m = fmaxf(m, mslot[(H ^ 1) * 128]);
+        const uint64_t one2 = tm_pack2(1.f, 1.f), negm2 = tm_pack2(-m, -m);
+        uint64_t l2 = 0ull;
+        float ev[SC];
+#pragma unroll
+        for (int j = 0; j < SC; j += 2) {
+          if (j + 1 < NV) {
+            float d0, d1;
+            tm_unpack2(tm_fma2(tm_pack2(__uint_as_float(mine[j]), __uint_as_float(mine[j + 1])), one2, negm2), d0, d1);
+            ev[j] = fast_exp2(d0);
+            ev[j + 1] = fast_exp2(d1);
+            l2 = tm_fma2(tm_pack2(ev[j], ev[j + 1]), one2, l2);
+          } else if (j < NV) {
+            ev[j] = fast_exp2(__uint_as_float(mine[j]) - m);
+            ev[j + 1] = 0.f;
+            l2 = tm_fma2(tm_pack2(ev[j], 0.f), one2, l2);
+          } else {
+            ev[j] = ev[j + 1] = 0.f;
+          }
+        }
+        float l0, l1;
+        tm_unpack2(l2, l0, l1);
+        tmem_st1(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2 + H, __float_as_uint(l0 + l1));
+        if constexpr (SC % 16 == 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 16) {
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (c0 + 2 * j < NV) split2_f16(ev[c0 + 2 * j], ev[c0 + 2 * j + 1], hi[j], lo[j]);
+              else hi[j] = lo[j] = 0u;
+            }
+            tmem_st8(ts + (base + c0) / 2, hi);
+            tmem_st8(ts + TP / 2 + (base + c0) / 2, lo);
+          }
+        } else {
+#pragma unroll
+          for (int c0 = 0; c0 < SC; c0 += 8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c0 + 2 * j < NV) split2_f16(ev[c0 + 2 * j], ev[c0 + 2 * j + 1], hi[j], lo[j]);
+              else hi[j] = lo[j] = 0u;
+            }
+            tmem_st4(ts + (base + c0) / 2, hi);
+            tmem_st4(ts + TP / 2 + (base + c0) / 2, lo);
+          }
+        }
+      };
+      if (half == 0) softmax_half(std::integral_constant<int, 0>{});
+      else softmax_half(std::integral_constant<int, 1>{});
+      wait_st();
+      fence_before_sync();
+      mbar_arrive(&bar_p_full[s]);   // release: l and P (TMEM) are visible to the consumers
+    }
+  } else if (warp < MMA_WARP) {
+    // ======================================================================== BACK (two threads per row)
+    const int bw = warp - 8;
+    const int rowgrp = bw & 3, half = bw >> 2;
+    const int row = rowgrp * 32 + lane;
+    const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
+    constexpr int RC = Cfg::kRoundCols;   // output columns staged per round
+    constexpr int HC = RC / 2;            // ... of which this thread owns a contiguous half
+    const bool bf16_out = p.out_dtype == NAF_DTYPE_BF16;
+    const bool issuer = tid == NFRONT;
+    if (issuer) {
+      tmap::prefetch_desc(&tmO);
+      tmap::prefetch_desc(&tmO2);
+    }
+    int n = 0;      // accumulator uses so far: (tile, half) pairs
+    int g = 0;
+    for (int it_seq = 0; it_seq < my_items; ++it_seq) {
+      const TmItem it = item_of(it_seq);
+      for (int tile = 0; tile < ntiles; ++tile, ++g) {
+        const bool last_tile = tile + 1 == ntiles;
+        const int y0 = it.ci * rh + tile * gm.th, x0 = it.cj * rw;
+        float inv_l = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh, ++n) {
+          mbar_wait(&bar_o_full, n & 1);
+          fence_after_sync();
+          if (hh == 0) {
+            uint32_t l0, l1;
+            tmem_ld2(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2, l0, l1);
+            wait_ld();
+            inv_l = 1.f / (__uint_as_float(l0) + __uint_as_float(l1));
+          }
+#pragma unroll
+          for (int rd = 0; rd < ROUNDS; ++rd) {
+            const uint32_t to = tmem + Cfg::kTmemO + lane_off + rd * RC + half * HC;
+            const uint64_t inv2 = tm_pack2(inv_l, inv_l);
+            // normalise 16 accumulator columns and write them into the swizzled box images
+            auto stage16 = [&](const uint32_t (&r)[16], int c) {
+              if (bf16_out) {
+                // 64 channels per 128-byte box row
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                  uint4 pk;
+                  uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[j + 2 * e]) * inv_l,
+                                                                    __uint_as_float(r[j + 2 * e + 1]) * inv_l);
+                    pw[e] = *reinterpret_cast<const uint32_t*>(&h2);
+                  }
+                  const int col = half * HC + c + j;
+                  *reinterpret_cast<uint4*>(stage_out + (col >> 6) * Cfg::kBox + tmap::swz128(row, (col & 63) >> 3)) = pk;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const uint64_t o01 = tm_fma2(tm_pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), inv2, 0ull);
+                  const uint64_t o23 = tm_fma2(tm_pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), inv2, 0ull);
+                  const int col = half * HC + c + j;
+                  *reinterpret_cast<uint4*>(stage_out + (col >> 5) * Cfg::kBox + tmap::swz128(row, (col & 31) >> 2)) =
+                      make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
+                }
+              }
+            };
+            if constexpr (HC <= 32) {
+              // narrow rounds (two accumulator halves per tile): pull the columns into registers first and hand
+              // O back to the tensor core BEFORE waiting for the staging area
+              uint32_t r[HC / 16][16];
+#pragma unroll
+              for (int c = 0; c < HC / 16; ++c) tmem_ld16(to + c * 16, r[c]);
+              wait_ld();
+              if (rd == ROUNDS - 1) {
+                fence_before_sync();
+                mbar_arrive(&bar_o_free);
+              }
+              if (issuer) bulk_wait_read<0>();   // the previous round's tensor stores have read the staging area
+              asm volatile("bar.sync 2, 256;" ::: "memory");
+#pragma unroll
+              for (int c = 0; c < HC / 16; ++c) stage16(r[c], c * 16);
+            } else {
+              if (issuer) bulk_wait_read<0>();
+              asm volatile("bar.sync 2, 256;" ::: "memory");
+              uint32_t r[2][16];
+              tmem_ld16(to, r[0]);
+#pragma unroll
+              for (int c = 0; c < HC / 16; ++c) {
+                wait_ld();
+                if (c + 1 < HC / 16) tmem_ld16(to + (c + 1) * 16, r[(c + 1) & 1]);
+                else if (rd == ROUNDS - 1) {
+                  // the whole accumulator is in registers / staged: the next PV may overwrite O
+                  fence_before_sync();
+                  mbar_arrive(&bar_o_free);
+                }
+                stage16(r[c & 1], c * 16);
+              }
+            }
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 3, 256;" ::: "memory");
+            if (issuer) {
+              const CUtensorMap* tm = (last_tile && gm.th_last != gm.th) ? &tmO2 : &tmO;
+              const int c0 = it.head * Cfg::DV + hh * DVH + rd * RC;
+              const int per_box = bf16_out ? 64 : 32;
+              const int nbox = RC / per_box;
+              for (int j = 0; j < nbox; ++j) tmap::store4(tm, c0 + j * per_box, x0, y0, it.b, stage_out + j * Cfg::kBox);
+              bulk_commit();
+            }
+          }
+        }
+      }
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output writes performed
+  } else if (warp == LOAD_WARP) {
+    // ======================================================================== WINDOW LOADER
+    if (lane == 0) {
+      tmap::prefetch_desc(&tmK);
+      tmap::prefetch_desc(&tmV);
+      for (int it_seq = 0; it_seq < my_items; ++it_seq) {
+        const TmItem it = item_of(it_seq);
+        const int wy0 = window_origin(it.ci, p.h, K), wx0 = window_origin(it.cj, p.w, K);
+        const int kb = it_seq & 1;
+        if (it_seq >= 2) mbar_wait(&bar_k_free[kb], ((it_seq >> 1) - 1) & 1);
+        mbar_expect_tx(&bar_k_full[kb], 2 * Cfg::kKPlane);
+        uint8_t* kdst = sK + kb * Cfg::kKWin;
+        const int gk = (it.b * 2) * gm.groups_k + it.head * KC;
+        tmap::load4(kdst, &tmK, 0, wx0, wy0, gk, &bar_k_full[kb]);
+        tmap::load4(kdst + Cfg::kKStride, &tmK, 0, wx0, wy0, gk + gm.groups_k, &bar_k_full[kb]);
+        const int vb = Cfg::NVB == 2 ? (it_seq & 1) : 0;
+        const int vuse = Cfg::NVB == 2 ? (it_seq >> 1) : it_seq;     // how often this buffer has been filled before
+        if (vuse >= 1) mbar_wait(&bar_v_free[vb], (vuse - 1) & 1);
+        mbar_expect_tx(&bar_v_full[vb], 2 * Cfg::kVPlane);
+        uint8_t* vdst = sV + vb * Cfg::kVWin;
+        const int gv = (it.b * 2) * gm.groups_v + it.head * (Cfg::DV / 8);
+        tmap::load4(vdst, &tmV, 0, wx0, wy0, gv, &bar_v_full[vb]);
+        tmap::load4(vdst + Cfg::kVStride, &tmV, 0, wx0, wy0, gv + gm.groups_v, &bar_v_full[vb]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================================================================== MMA ISSUER
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc_f16(128, TP, false, false);
+      constexpr uint32_t idesc_pv = make_idesc_f16(128, DVH, false, true);
+      const uint32_t tO = tmem + Cfg::kTmemO;
+      constexpr int QS = Cfg::kQStages;
+      int qk_seq = 0, qk_tile = 0, pv_seq = 0, pv_tile = 0;   // (item, tile) of the next QK / PV
+      int n = 0;                                              // accumulator uses issued so far
+      auto issue_qk = [&](int g) {
+        const int s = g & 1;
+        const int it_seq = qk_seq;
+        const int kb = it_seq & 1;
+        if (qk_tile == 0) {
+          mbar_wait(&bar_k_full[kb], (it_seq >> 1) & 1);
+        }
+        const uint8_t* w = sK + kb * Cfg::kKWin;
+        const bool last_of_item = qk_tile + 1 == ntiles;
+        if (++qk_tile == ntiles) { qk_tile = 0; ++qk_seq; }
+        if constexpr (QS == 2) mbar_wait(&bar_q_full[s], (g >> 1) & 1);
+        else mbar_wait(&bar_q_full[0], g & 1);
+        fence_after_sync();
+        const uint32_t tq = tmem + Cfg::kTmemQ + (QS == 2 ? s * 64 : 0);
+        const uint32_t tS = tmem + Cfg::kTmemS + s * TP;
+        // S = Qhi*Khi^T + Qlo*Khi^T + Qhi*Klo^T
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = tq + (pass == 1 ? 32 : 0);
+          const uint32_t b0 = smem_u32(w + (pass == 2 ? Cfg::kKStride : 0));
+#pragma unroll
+          for (int kk = 0; kk < DQ / 16; ++kk) {
+            // K-major B: 16 channels = 2 channel groups per MMA; LBO = one channel-group plane, SBO = 8 taps
+            const uint64_t db = make_desc(b0 + kk * 2 * (K2 * 16), K2 * 16, 128);
+            mma_f16_ts(tS, a0 + kk * 8, db, idesc_qk, (pass | kk) != 0);
+          }
+        }
+        commit(&bar_s_full[s]);
+        if (last_of_item) commit(&bar_k_free[kb]);   // every MMA reading this K window has been issued
+      };
+      auto issue_pv = [&](int g) {
+        const int s = g & 1;
+        mbar_wait(&bar_p_full[s], (g >> 1) & 1);
+        const int vb = Cfg::NVB == 2 ? (pv_seq & 1) : 0;
+        const int vuse = Cfg::NVB == 2 ? (pv_seq >> 1) : pv_seq;
+        if (pv_tile == 0) mbar_wait(&bar_v_full[vb], vuse & 1);
+        const uint8_t* w = sV + vb * Cfg::kVWin;
+        const bool last_of_item = pv_tile + 1 == ntiles;
+        if (++pv_tile == ntiles) { pv_tile = 0; ++pv_seq; }
+        const uint32_t tP = tmem + Cfg::kTmemS + s * TP;
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh, ++n) {
+          mbar_wait(&bar_o_free, (n + 1) & 1);   // O drained by the epilogue of the previous use
+          fence_after_sync();
+          // O = Phi*Vhi + Plo*Vhi + Phi*Vlo on the channel groups of this half
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a0 = tP + (pass == 1 ? TP / 2 : 0);
+            const uint32_t b0 = smem_u32(w + (pass == 2 ? Cfg::kVStride : 0) + hh * (DVH / 8) * (K2 * 16));
+#pragma unroll
+            for (int kk = 0; kk < TP / 16; ++kk) {
+              // MN-major B: 16 taps = 2 groups of 8 taps per MMA; LBO = 8 taps, SBO = one channel-group plane
+              const uint64_t db = make_desc(b0 + kk * 256, 128, K2 * 16);
+              mma_f16_ts(tO, a0 + kk * 8, db, idesc_pv, (pass | kk) != 0);
+            }
+          }
+          commit(&bar_o_full);
+        }
+        if (last_of_item) commit(&bar_v_free[vb]);
+      };
+      if (total_tiles > 0) issue_qk(0);
+      for (int g = 0; g < total_tiles; ++g) {
+        if (g + 1 < total_tiles) issue_qk(g + 1);
+        issue_pv(g);
+      }
+    }
+    __syncwarp();
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------ host side
+namespace {
+
+int tm_taps_pad(int K) { return (K * K + 15) / 16 * 16; }
+
+TmFastDiv tm_make_div(uint32_t d) {
+  TmFastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  if ((d & (d - 1)) == 0) {
+    f.magic = 0;
+    f.shift = s;
+  } else {
+    f.magic = uint32_t(((uint64_t(1) << (31 + s)) + d - 1) / d);
+    f.shift = s - 1;
+  }
+  return f;
+}
+
+// tile geometry: whole cell rows, balanced
+void tm_tiles(int rh, int rw, int& th, int& ntiles, int& th_last) {
+  th = 128 / rw;
+  if (th < 1) th = 1;
+  if (th > rh) th = rh;
+  ntiles = (rh + th - 1) / th;
+  th = (rh + ntiles - 1) / ntiles;
+  ntiles = (rh + th - 1) / th;
+  th_last = rh - (ntiles - 1) * th;
+}
+
+size_t tm_workspace_bytes(const naf_xattn_params& p) {
+  // fp16 hi + lo planes of K and V: the same byte count as the fp32 maps
+  return size_t(p.B) * p.h * p.w * (size_t(p.D) + p.C) * 4 + 256;
+}
+
+template <int TP, int DVH, int NH, int ROUNDS>
+int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
+  using Cfg = TmaCfg<TP, DVH, NH, ROUNDS>;
+  if constexpr (!Cfg::kFits) {
+    return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): tile %dx%dx%d/%d does not fit", TP, DVH, NH, ROUNDS);
+  } else {
+    auto kern = xattn_cell_tma_kernel<TP, DVH, NH, ROUNDS>;
+    cudaError_t e = ensure_dyn_smem(kern, Cfg::kSmemBytes);
+    if (e != cudaSuccess)
+      return fail(NAF_ERR_CUDA, "xattn(cell-tma): smem opt-in failed: %s", cudaGetErrorString(e));
+    const int sms = device_sm_count();
+    TmGeom gm;
+    gm.rh = p.Ho / p.h;
+    gm.rw = p.Wo / p.w;
+    tm_tiles(gm.rh, gm.rw, gm.th, gm.ntiles, gm.th_last);
+    const int64_t items = int64_t(p.B) * p.h * p.w * p.heads;
+    gm.n_items = int(items);
+    gm.groups_k = p.D / 8;
+    gm.groups_v = p.C / 8;
+    TmDivs dv;
+    dv.ntiles = tm_make_div(uint32_t(gm.ntiles));
+    dv.heads = tm_make_div(uint32_t(p.heads));
+    dv.w = tm_make_div(uint32_t(p.w));
+    dv.h = tm_make_div(uint32_t(p.h));
+    dv.rw = tm_make_div(uint32_t(gm.rw));
+    dv.rep_y = tm_make_div(uint32_t(p.rep_y));
+    dv.rep_x = tm_make_div(uint32_t(p.rep_x));
+
+    // ---- pre-pass: K and V -> fp16 hi / lo channel-group planes in the caller's workspace
+    uint8_t* ws = static_cast<uint8_t*>(p.workspace);
+    ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~uintptr_t(127));
+    uint8_t* kplanes = ws;
+    uint8_t* vplanes = ws + size_t(p.B) * p.h * p.w * p.D * 4;
+    prefer_max_shared(kv_planes_kernel);
+    {
+      const int64_t nk = int64_t(p.B) * (p.D / 8) * p.h * p.w, nv = int64_t(p.B) * (p.C / 8) * p.h * p.w;
+      const int64_t cap = int64_t(sms) * 16;
+      const int64_t bk_ = (nk + 255) / 256, bv_ = (nv + 255) / 256;
+      const unsigned gk_ = unsigned(bk_ < cap ? bk_ : cap), gv_ = unsigned(bv_ < cap ? bv_ : cap);
+      kv_planes_kernel<<<gk_, 256, 0, st>>>(p.k, reinterpret_cast<uint4*>(kplanes), p.B, p.h, p.w, p.D);
+      kv_planes_kernel<<<gv_, 256, 0, st>>>(p.v, reinterpret_cast<uint4*>(vplanes), p.B, p.h, p.w, p.C);
+      int rc = check_launch("xattn_kv_planes");
+      if (rc != NAF_OK) return rc;
+    }
+    // ---- tensor maps
+    CUtensorMap tmK, tmV, tmO, tmO2;
+    {
+      const uint64_t dk[4] = {8, uint64_t(p.w), uint64_t(p.h), uint64_t(p.B) * 2 * (p.D / 8)};
+      const uint64_t dvv[4] = {8, uint64_t(p.w), uint64_t(p.h), uint64_t(p.B) * 2 * (p.C / 8)};
+      const uint64_t sp[3] = {16, uint64_t(p.w) * 16, uint64_t(p.h) * p.w * 16};
+      const uint32_t bk[4] = {8, uint32_t(Cfg::K), uint32_t(Cfg::K), uint32_t(KC)};
+      const uint32_t bv[4] = {8, uint32_t(Cfg::K), uint32_t(Cfg::K), uint32_t(Cfg::DV / 8)};
+      const bool bf16 = p.out_dtype == NAF_DTYPE_BF16;
+      const uint64_t es = bf16 ? 2 : 4;
+      const uint64_t d_o[4] = {uint64_t(p.C), uint64_t(p.Wo), uint64_t(p.Ho), uint64_t(p.B)};
+      const uint64_t so[3] = {uint64_t(p.C) * es, uint64_t(p.Wo) * p.C * es, uint64_t(p.Ho) * p.Wo * p.C * es};
+      const uint32_t bo[4] = {bf16 ? 64u : 32u, uint32_t(gm.rw), uint32_t(gm.th), 1};
+      const uint32_t bo2[4] = {bf16 ? 64u : 32u, uint32_t(gm.rw), uint32_t(gm.th_last), 1};
+      const CUtensorMapDataType odt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+      if (!tmap::encode4(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, kplanes, dk, sp, bk, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+          !tmap::encode4(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, vplanes, dvv, sp, bv, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+          !tmap::encode4(&tmO, odt, p.out, d_o, so, bo, CU_TENSOR_MAP_SWIZZLE_128B) ||
+          !tmap::encode4(&tmO2, odt, p.out, d_o, so, bo2, CU_TENSOR_MAP_SWIZZLE_128B))
+        return fail(NAF_ERR_CUDA, "xattn(cell-tma): cuTensorMapEncodeTiled failed");
+    }
+    const int grid = int(items < sms ? items : sms);
+    kern<<<grid, NTHREADS, Cfg::kSmemBytes, st>>>(p, gm, dv, tmK, tmV, tmO, tmO2);
+    return check_launch("xattn_cell_tma");
+  }
+}
+
+// (value head dim) -> (DVH, NH, ROUNDS) per padded tap count; 0 = no configuration
+struct TmPlan {
+  int dvh = 0, nh = 0, rounds = 0;
+};
+
+template <int TP>
+constexpr TmPlan tm_plan(int dv) {
+  // whole head in one accumulator when TMEM and shared memory allow, else two halves against one P
+  TmPlan pl;
+  switch (dv) {
+    case 32: if (TmaCfg<TP, 32, 1, 1>::kFits) pl = {32, 1, 1}; break;
+    case 64: if (TmaCfg<TP, 64, 1, 1>::kFits) pl = {64, 1, 1}; break;
+    case 96: if (TmaCfg<TP, 96, 1, 1>::kFits) pl = {96, 1, 1}; break;
+    case 128: if (TmaCfg<TP, 128, 1, 1>::kFits) pl = {128, 1, 1}; else if (TmaCfg<TP, 64, 2, 1>::kFits) pl = {64, 2, 1}; break;
+    case 192: if (TmaCfg<TP, 192, 1, 1>::kFits) pl = {192, 1, 1}; else if (TmaCfg<TP, 96, 2, 1>::kFits) pl = {96, 2, 1}; break;
+    case 256: if (TmaCfg<TP, 256, 1, 1>::kFits) pl = {256, 1, 1}; else if (TmaCfg<TP, 128, 2, 1>::kFits) pl = {128, 2, 1};
+              else if (TmaCfg<TP, 128, 2, 2>::kFits) pl = {128, 2, 2}; break;
+    default: break;
+  }
+  return pl;
+}
+
+TmPlan tm_plan_for(int K, int dv) {
+  switch (tm_taps_pad(K)) {
+    case 16: return tm_plan<16>(dv);
+    case 32: return tm_plan<32>(dv);
+    case 64: return tm_plan<64>(dv);
+    case 96: return tm_plan<96>(dv);
+    case 128: return tm_plan<128>(dv);
+    default: return TmPlan{};
+  }
+}
+
+template <int TP, int DVFULL>
+int launch_tma_dv(const naf_xattn_params& p, cudaStream_t st) {
+  constexpr TmPlan pl = tm_plan<TP>(DVFULL);
+  if constexpr (pl.dvh == 0) {
+    return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): no plan for dv=%d", DVFULL);
+  } else {
+    return launch_tma<TP, pl.dvh, pl.nh, pl.rounds>(p, st);
+  }
+}
+
+template <int TP>
+int launch_tma_tp(const naf_xattn_params& p, cudaStream_t st) {
+  switch (p.C / p.heads) {
+    case 32: return launch_tma_dv<TP, 32>(p, st);
+    case 64: return launch_tma_dv<TP, 64>(p, st);
+    case 96: return launch_tma_dv<TP, 96>(p, st);
+    case 128: return launch_tma_dv<TP, 128>(p, st);
+    case 192: return launch_tma_dv<TP, 192>(p, st);
+    case 256: return launch_tma_dv<TP, 256>(p, st);
+    default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): no plan for dv=%d", p.C / p.heads);
+  }
+}
+
+}  // namespace
+
+size_t xattn_cell_tma_workspace(const naf_xattn_params& p) { return tm_workspace_bytes(p); }
+
+bool xattn_cell_tma_supported(const naf_xattn_params& p, const char** why) {
+  const int dq = p.D / p.heads, dv = p.C / p.heads;
+  if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
+  if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }
+  if (p.scores) { *why = "score output requested"; return false; }
+  if (dq != DQ) { *why = "head dim must be 64"; return false; }
+  if (p.K < 3 || p.K > 11) { *why = "kernel_size must be 3, 5, 7, 9 or 11"; return false; }
+  if (p.h < p.K || p.w < p.K) { *why = "feature map smaller than the window"; return false; }
+  const TmPlan pl = tm_plan_for(p.K, dv);
+  if (!pl.dvh) { *why = "no tile configuration for this window / value head dim"; return false; }
+  const int rh = p.Ho / p.h, rw = p.Wo / p.w;
+  if (rw > 128) { *why = "cells wider than 128 pixels"; return false; }
+  if (rh * rw < 64) { *why = "fewer than 64 pixels per cell"; return false; }
+  if (p.out_dtype == NAF_DTYPE_BF16 && ((pl.dvh / pl.rounds) % 64 || p.C % 8)) { *why = "bf16 store needs 64-channel boxes"; return false; }
+  if (!p.workspace || size_t(p.workspace_bytes) < tm_workspace_bytes(p)) { *why = "workspace missing or too small (naf_xattn_workspace_bytes)"; return false; }
+  if (!aligned32(p.q) || !aligned32(p.k) || !aligned32(p.v) || !aligned16(p.out) || (p.C % 4) ||
+      (p.q_stride_b % 8) || (p.q_stride_y % 8) || (p.q_stride_x % 8)) {
+    *why = "pointers/strides not aligned";
+    return false;
+  }
+  if (p.cos_y && !(aligned32(p.cos_y) && aligned32(p.sin_y) && aligned32(p.cos_x) && aligned32(p.sin_x))) {
+    *why = "rope tables not 32-byte aligned";
+    return false;
+  }
+  if (int64_t(p.B) * p.h * p.w * p.heads >= (int64_t(1) << 31)) { *why = "too many items"; return false; }
+  if (int64_t(p.B) * 2 * (p.C / 8) >= (int64_t(1) << 31)) { *why = "too many planes"; return false; }
+  if (!tmap::encode_fn()) { *why = "cuTensorMapEncodeTiled not available from the driver"; return false; }
+  return true;
+}
+
+int launch_xattn_cell_tma(const naf_xattn_params& p, cudaStream_t st) {
+  switch (tm_taps_pad(p.K)) {
+    case 16: return launch_tma_tp<16>(p, st);
+    case 32: return launch_tma_tp<32>(p, st);
+    case 64: return launch_tma_tp<64>(p, st);
+    case 96: return launch_tma_tp<96>(p, st);
+    case 128: return launch_tma_tp<128>(p, st);
+    default: return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): kernel_size %d", p.K);
+  }
+}
+
+}  // namespace naf

@@ -143,6 +143,9 @@ class NAF(nn.Module):
         Ho, Wo = x.shape[-2] * rep[0], x.shape[-1] * rep[1]
         tables = rope.axis_tables(Ho, Wo)
         D = x.shape[1]
+        if out_dtype is None:
+            from ..layers.attentions import autocast_out_dtype
+            out_dtype = autocast_out_dtype()
         fused = rope.D_head == D // self.upsampler.num_heads
         h, w = features.shape[-2:]
         ry, rx = int(rep[0]), int(rep[1])
@@ -184,16 +187,20 @@ class NAF(nn.Module):
         """`out_dtype`: None = what the reference returns in this context (bf16 under bf16 autocast,
         else fp32); torch.float32 / torch.bfloat16 to choose.  All arithmetic is fp32 either way.
 
-        With grad mode on and anything that requires grad (the parameters in a training loop,
-        train.py:127-136; the features or the image when a backbone or a probe is trained through a
-        frozen NAF) the call is differentiable like the reference's: the conv encoder runs as plain torch
-        modules under autograd (cuDNN), the attention path through `naf_b200.autograd.NAFUpsampleFn`
-        (our forward AND backward kernels).  Otherwise: the inference path, all on our kernels."""
+        With grad mode on the call is differentiable like the reference's when there is something to
+        differentiate: the module is in train() mode with trainable parameters (a training loop,
+        train.py:127-136), or the features / the image require grad (a backbone or a probe trained through
+        a frozen NAF).  The conv encoder then runs as plain torch modules under autograd (cuDNN), the
+        attention path through `naf_b200.autograd.NAFUpsampleFn` (our forward AND backward kernels).
+        Otherwise -- including eval() mode with grad mode left on and only the parameters requiring
+        grad, which every reference eval caller avoids with no_grad -- the inference path runs, all on
+        our kernels, and the result is detached (the parameters are treated as frozen)."""
         from ..layers.attentions import autocast_out_dtype
         if out_dtype is None:
             out_dtype = autocast_out_dtype()
-        needs_grad = torch.is_grad_enabled() and (features.requires_grad or image.requires_grad or
-                                                  any(p.requires_grad for p in self.parameters()))
+        needs_grad = torch.is_grad_enabled() and (
+            features.requires_grad or image.requires_grad or
+            (self.training and any(p.requires_grad for p in self.parameters())))
         if needs_grad:
             enc = self.image_encoder
             Ho, Wo = int(output_size[0]), int(output_size[1])

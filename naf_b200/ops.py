@@ -276,6 +276,12 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_
     scores = (torch.empty((B, heads, Ho, Wo, K * K), device=dev, dtype=torch.float32)
               if return_scores else None)
     p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo, rep)
+    # scratch for the TMA kernel's fp16 K / V planes (the C side never allocates); freed to the caching
+    # allocator when this function returns -- stream-ordered, so the enqueued kernels still own it
+    ws_bytes = int(_lib.load().naf_xattn_workspace_bytes(C.byref(p)))
+    if ws_bytes:
+        ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+        p.workspace, p.workspace_bytes = _ptr(ws), ws_bytes
     _launch_xattn(p, dev)
     res = out.permute(0, 3, 1, 2)
     return (res, scores) if return_scores else res
@@ -379,6 +385,7 @@ def select_algo(q_shape, v_shape, heads: int, kernel_size: int, rope_on_the_fly:
     p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
     p.scale = (D // heads) ** -0.5
     p.q_stride_b, p.q_stride_y, p.q_stride_x = Ho * Wo * D, Wo * D, D
+    p.workspace, p.workspace_bytes = dummy, 1 << 62     # as ops.xattn provides it
     rc = _lib.load().naf_xattn_select_algo(C.byref(p))
     if rc < 0:
         _lib.check(-rc, "naf_xattn_select_algo")

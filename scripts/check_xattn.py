@@ -6,7 +6,7 @@ import torch
 import naf_b200
 from naf_b200 import ops
 a = sys.argv[1:]
-algo = {"auto": 0, "generic": 1, "cell_simt": 2, "cell_tc": 3, "cell_tcws": 4}[a[0]]
+algo = {"auto": 0, "generic": 1, "cell_simt": 2, "cell_tc": 3, "cell_tcws": 4, "cell_tma": 5}[a[0]]
 B, C, to, lo, K = (int(a[i]) if len(a) > i else d for i, d in ((1, 2), (2, 768), (3, 224), (4, 8), (5, 7)))
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)

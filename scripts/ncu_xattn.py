@@ -6,7 +6,7 @@ import naf_b200
 from naf_b200 import _lib, ops
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-algo = {"auto": 0, "generic": 1, "cell_simt": 2, "cell_tc": 3, "cell_tcws": 4}[sys.argv[2] if len(sys.argv) > 2 else "auto"]
+algo = {"auto": 0, "generic": 1, "cell_simt": 2, "cell_tc": 3, "cell_tcws": 4, "cell_tma": 5}[sys.argv[2] if len(sys.argv) > 2 else "auto"]
 C, to, lo, K = 768, 896, 32, 7
 rep = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 dev = torch.device("cuda", 0)

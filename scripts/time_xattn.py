@@ -8,7 +8,7 @@ from naf_b200 import ops
 
 a = sys.argv[1:]
 B = int(a[0]) if len(a) > 0 else 8
-algo = {"auto": 0, "generic": 1, "cell_simt": 2, "cell_tc": 3, "cell_tcws": 4}[a[1] if len(a) > 1 else "auto"]
+algo = {"auto": 0, "generic": 1, "cell_simt": 2, "cell_tc": 3, "cell_tcws": 4, "cell_tma": 5}[a[1] if len(a) > 1 else "auto"]
 C, to, lo, K, rep = (int(a[i]) if len(a) > i else d for i, d in ((2, 768), (3, 896), (4, 32), (5, 7), (6, 1)))
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)

@@ -97,10 +97,11 @@ tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, const float* __r
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x;
   const int npix = th * tw;
+  const int box_stride = (npix * 128 + 1023) / 1024 * 1024;   // every box image 1024-byte aligned (swizzle atom)
   // thread <-> pixel of the tile (row-major), as the attention epilogue (thread <-> TMEM lane)
   if (tid < npix) {
     for (int j = 0; j < NB; ++j) {
-      uint8_t* boxp = smem + size_t(j) * npix * 128;
+      uint8_t* boxp = smem + size_t(j) * box_stride;
       for (int c = 0; c < 8; ++c) {
         const float4 v = *reinterpret_cast<const float4*>(src + (size_t(tid) * NB + j) * 32 + c * 4);
         *reinterpret_cast<float4*>(boxp + tmx::swz128(tid, c)) = v;
@@ -110,7 +111,7 @@ tma_store_probe_kernel(const __grid_constant__ CUtensorMap map, const float* __r
   fence_proxy_async_smem();
   __syncthreads();
   if (tid == 0) {
-    for (int j = 0; j < NB; ++j) tmx::store4(&map, c0 + 32 * j, x0, y0, b, smem + size_t(j) * npix * 128);
+    for (int j = 0; j < NB; ++j) tmx::store4(&map, c0 + 32 * j, x0, y0, b, smem + size_t(j) * box_stride);
     bulk_commit();
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
@@ -125,7 +126,7 @@ int tma_store_probe(float* out, int B, int Ho, int Wo, int C, const float* src, 
   const uint32_t box[4] = {32, uint32_t(tw), uint32_t(th), 1};
   if (!tmx::encode4(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, out, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
     return -1;
-  const size_t smem = size_t(NB) * th * tw * 128 + 1024;
+  const size_t smem = size_t(NB) * ((th * tw * 128 + 1023) / 1024 * 1024) + 1024;
   cudaFuncSetAttribute(tma_store_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   tma_store_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(map, src, th, tw, NB, c0, x0, y0, b);
   return int(cudaGetLastError());

@@ -58,7 +58,7 @@ int main(void){
 
 def test_kernel_selection_for_baseline_configs():
     sel = ops.select_algo
-    fast = {"cell_simt", "cell_tcws"}
+    fast = {"cell_simt", "cell_tcws", "cell_tma"}
     assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7) in fast      # C1
     assert sel((8, 256, 896, 896), (8, 768, 32, 32), 4, 7) in fast      # C2
     assert sel((4, 256, 1036, 1036), (4, 1024, 37, 37), 4, 11) in fast  # C3

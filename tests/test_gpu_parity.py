@@ -26,7 +26,7 @@ def dev():
 
 
 def tol_for(algo):
-    return TOL_BAR if algo == _lib.ALGO_CELL_TCWS else TOL_FP32
+    return TOL_BAR if algo in (_lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA) else TOL_FP32
 
 
 def available_algos(q_shape, v_shape, heads, K):
@@ -34,10 +34,11 @@ def available_algos(q_shape, v_shape, heads, K):
     algos = [_lib.ALGO_GENERIC]
     Ho, Wo, h, w = q_shape[2], q_shape[3], v_shape[2], v_shape[3]
     if Ho % h == 0 and Wo % w == 0:
-        for algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TCWS):
+        for algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA):
             p = _lib.XAttnParams()
             d = 1 << 20
             p.q = p.k = p.v = p.out = d
+            p.workspace, p.workspace_bytes = d, 1 << 62
             p.B, p.D, p.C, p.heads = q_shape[0], q_shape[1], v_shape[1], heads
             p.Ho, p.Wo, p.h, p.w, p.K = Ho, Wo, h, w, K
             p.scale = 1.0
