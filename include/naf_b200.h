@@ -150,6 +150,11 @@ typedef struct naf_xattn_params {
   void* workspace;       /* scratch the TMA kernel keeps its fp16 hi/lo K and V planes in (>= naf_xattn_workspace_bytes,
                             any alignment; contents undefined before and after the call); NULL: AUTO skips that kernel */
   int64_t workspace_bytes;
+  int32_t q_dtype, k_dtype, v_dtype; /* NAF_DTYPE_F32 (0) or NAF_DTYPE_BF16 (1): element type of q, k and v (same layouts,
+                            strides in elements).  bf16 is what the reference feeds under torch.autocast(bfloat16)
+                            (train.py:120); it is read as it is by the TMA kernel (NAF_ALGO_CELL_TMA) -- the other
+                            kernels take fp32 only and refuse (callers widen for them). */
+  int32_t reserved_;
 } naf_xattn_params;
 
 enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1 };

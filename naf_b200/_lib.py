@@ -53,6 +53,7 @@ class XAttnParams(C.Structure):
         ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
         ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32), ("out_dtype", C.c_int32),
         ("workspace", _fp), ("workspace_bytes", C.c_int64),
+        ("q_dtype", C.c_int32), ("k_dtype", C.c_int32), ("v_dtype", C.c_int32), ("reserved_", C.c_int32),
     ]
 
     def __init__(self, *a, **kw):

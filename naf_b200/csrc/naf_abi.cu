@@ -123,11 +123,19 @@ static int validate_xattn(const naf_xattn_params& p) {
               p.rep_y, p.rep_x);
   NAF_REQUIRE(p.out_dtype == NAF_DTYPE_F32 || p.out_dtype == NAF_DTYPE_BF16, NAF_ERR_UNSUPPORTED,
               "xattn: out_dtype %d (0 = f32, 1 = bf16)", p.out_dtype);
+  for (int dt : {p.q_dtype, p.k_dtype, p.v_dtype})
+    NAF_REQUIRE(dt == NAF_DTYPE_F32 || dt == NAF_DTYPE_BF16, NAF_ERR_UNSUPPORTED, "xattn: input dtype %d (0 = f32, 1 = bf16)", dt);
   return NAF_OK;
 }
 
 static int select_algo(const naf_xattn_params& p, bool explain) {
   const char* why = "";
+  if (p.q_dtype != NAF_DTYPE_F32 || p.k_dtype != NAF_DTYPE_F32 || p.v_dtype != NAF_DTYPE_F32) {
+    // bf16 inputs: only the TMA kernel reads them natively
+    if ((p.algo == NAF_ALGO_AUTO || p.algo == NAF_ALGO_CELL_TMA) && xattn_cell_tma_supported(p, &why)) return NAF_ALGO_CELL_TMA;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: bf16 inputs are read natively by the TMA cell kernel only (%s); pass fp32 "
+                                       "tensors to the other kernels", why);
+  }
   if (p.algo == NAF_ALGO_GENERIC) return NAF_ALGO_GENERIC;
   if (p.algo == NAF_ALGO_CELL_TMA) {
     if (xattn_cell_tma_supported(p, &why)) return NAF_ALGO_CELL_TMA;

@@ -46,6 +46,9 @@ constexpr int DQ = 64;
 constexpr int KC = DQ / 8;
 constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 64;
 constexpr int MMA_WARP = (NFRONT + NBACK) / 32, LOAD_WARP = MMA_WARP + 1;
+#ifndef NAF_TMA_EXP
+#define NAF_TMA_EXP 0   // profiling variants (scripts/build_variant.py): 1 = no output stores, 2 = no q loads,
+#endif                  // 4 = softmax without the exponentials (P = 1 on the valid taps)
 constexpr int kSmemLimit = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (static barriers extra)
 
 template <int TP>
@@ -68,12 +71,16 @@ struct TmaCfg {
   static constexpr int kVWin = 2 * kVStride;
   static constexpr int kRoundCols = DVH / ROUNDS;               // output columns staged per round
   static constexpr int kBox = 128 * 128;                        // one staging box image: 128 rows x 128 B
-  static constexpr int kStage = (kRoundCols / 32) * kBox;       // fp32: 32 channels per box (bf16: 64, half the boxes)
+  static constexpr int kSlot = (kRoundCols / 32) * kBox;        // one staging slot: a round's boxes (fp32: 32 channels per
+                                                                // box; bf16: 64, half the boxes)
   static constexpr int kMx = 2 * 2 * 128 * 4;                   // row-max exchange between the two row halves
   static constexpr int NKB = 2;
-  static constexpr int kFixed = NKB * kKWin + kStage + kMx;
-  static constexpr int NVB = (kFixed + 2 * kVWin <= kSmemLimit) ? 2 : 1;
-  static constexpr int kSmemTotal = kFixed + NVB * kVWin;
+  static constexpr int kMin = NKB * kKWin + kVWin + kSlot + kMx + 1024;   // one V buffer, one staging slot
+  // what is left goes first to a second staging slot (the tensor stores of round r read slot r&1 while round
+  // r+1 is drained into the other one), then to a second V window buffer
+  static constexpr int NSTG = (kMin + kSlot <= kSmemLimit) ? 2 : 1;
+  static constexpr int kStage = NSTG * kSlot;
+  static constexpr int NVB = (kMin + (NSTG - 1) * kSlot + kVWin <= kSmemLimit) ? 2 : 1;
   static constexpr int kOffK = 0;
   static constexpr int kOffV = NKB * kKWin;
   static constexpr int kOffStage = round_up(kOffV + NVB * kVWin, 1024);
@@ -141,9 +148,23 @@ struct TmGeom {
 
 }  // namespace
 
-// ---- pre-pass: fp32 (B,h,w,Cn) map -> fp16 hi / lo channel-group planes (B, 2, Cn/8, h, w, 8) ----------
+// ---- pre-pass: fp32 or bf16 (B,h,w,Cn) map -> fp16 hi / lo channel-group planes (B, 2, Cn/8, h, w, 8) ----
+// bf16 inputs (the reference under torch.autocast(bfloat16), train.py:120) are read as they are: no widened
+// copy of the features is ever made.
+__device__ __forceinline__ void load8_as_float(const float* p, float (&v)[8]) { ldg8(p, v); }
+__device__ __forceinline__ void load8_as_float(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-kv_planes_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, int h, int w, int Cn) {
+kv_planes_kernel(const T* __restrict__ src, uint4* __restrict__ dst, int B, int h, int w, int Cn) {
   const int G = Cn / 8;
   const int64_t total = int64_t(B) * G * h * w;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -155,7 +176,7 @@ kv_planes_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, 
     const int g = int(r % G);
     const int b = int(r / G);
     float v[8];
-    ldg8(src + ((int64_t(b) * h + y) * w + x) * Cn + g * 8, v);
+    load8_as_float(src + ((int64_t(b) * h + y) * w + x) * Cn + g * 8, v);
     uint4 hi, lo;
     split2_f16(v[0], v[1], hi.x, lo.x);
     split2_f16(v[2], v[3], hi.y, lo.y);
@@ -167,10 +188,9 @@ kv_planes_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int B, 
   }
 }
 
-// 18 warps x 112 registers = 64512 <= 65536 (ptxas settles for 96 under __launch_bounds__(576, 1) and spills
-// the 128-tap softmax rows)
+// 18 warps: one SM sub-partition (16 K registers) hosts 5 of them, hence at most 96 registers per thread
 template <int TP, int DVH, int NH, int ROUNDS>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(NTHREADS, 1)
 xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmO2) {
@@ -234,6 +254,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
     constexpr int HALF = DQ / 2, P = DQ / 4, SC = TP / 2;
     const bool rope = p.cos_y != nullptr;
+    const bool q_bf16 = p.q_dtype == NAF_DTYPE_BF16;
     const float qscale = p.scale * 1.4426950408889634f;
 
     float qa[P], qb[P];
@@ -250,12 +271,28 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
       const int py = tm_div(pi, dv.rw);
       q_y = it.ci * rh + py;
       q_x = it.cj * rw + (pi - py * rw);
-      const float* qp = p.q + int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
-                        int64_t(tm_div(q_y, dv.rep_y)) * p.q_stride_y + int64_t(tm_div(q_x, dv.rep_x)) * p.q_stride_x;
-      ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
-      ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
-      ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
-      ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+      const int64_t qoff = int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
+                           int64_t(tm_div(q_y, dv.rep_y)) * p.q_stride_y + int64_t(tm_div(q_x, dv.rep_x)) * p.q_stride_x;
+#if NAF_TMA_EXP & 2
+#pragma unroll
+      for (int j = 0; j < P; ++j) { qa[j] = 0.01f * float(j + (pi & 7)); qb[j] = -0.02f * float(j); }
+      (void)qoff;
+#else
+      if (q_bf16) {
+        // 16 bf16 channels = 32 bytes per rotation half
+        const __nv_bfloat16* qp = reinterpret_cast<const __nv_bfloat16*>(p.q) + qoff;
+        load8_as_float(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
+        load8_as_float(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
+        load8_as_float(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
+        load8_as_float(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+      } else {
+        const float* qp = p.q + qoff;
+        ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
+        ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
+        ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
+        ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+      }
+#endif
     };
     // rotate + scale + split the prefetched q and write it to TMEM:
     // columns [0,32) hi, [32,64) lo; two channels per 32-bit column
@@ -317,10 +354,10 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
       mbar_wait(&bar_s_full[s], (g >> 1) & 1);
       fence_after_sync();
       if constexpr (QS == 1) {
-        if (g + 1 < total_tiles) {
-          stage_q(g + 1);
-          if (g + 2 < total_tiles) issue_q();
-        }
+        // one Q stage (128-tap windows): the prefetch of tile g+2 is issued AFTER the softmax below, so that the
+        // 32 query registers are not live across it (the 64-value softmax rows need the registers; the loads
+        // still have QK(g+1) plus the wait for it to complete)
+        if (g + 1 < total_tiles) stage_q(g + 1);
       }
       const uint32_t ts = tmem + Cfg::kTmemS + s * TP + lane_off;
       auto softmax_half = [&](auto half_c) {
@@ -339,6 +376,20 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         float m = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NV; ++j) m = fmaxf(m, __uint_as_float(mine[j]));
+        if (p.scores != nullptr) {
+          // return_weights=True (src/layers/attentions.py:27-28): the scaled pre-softmax logits, tap order
+          // t_h*K + t_w.  S holds them times log2(e) (folded into the query scale for the exp2 softmax).
+          const int it_s = tm_div(g, dv.ntiles), tile_s = g - it_s * ntiles;
+          const TmItem its = item_of(it_s);
+          const int pi = tile_s * tile_rows + row;
+          if (pi < min(npix, (tile_s + 1) * tile_rows)) {
+            const int py = tm_div(pi, dv.rw);
+            const int y = its.ci * rh + py, x = its.cj * rw + (pi - py * rw);
+            float* so = p.scores + (((int64_t(its.b) * p.heads + its.head) * p.Ho + y) * p.Wo + x) * K2 + base;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) so[j] = __uint_as_float(mine[j]) * 0.6931471805599453f;
+          }
+        }
         // the two halves of a row exchange their partial maxima through shared memory; the same named
         // barrier orders the S reads of both halves before P overwrites the S columns
         float* mslot = mx + (s * 2) * 128 + row;
@@ -349,57 +400,53 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         m = fmaxf(m, mslot[(H ^ 1) * 128]);
         const uint64_t one2 = tm_pack2(1.f, 1.f), negm2 = tm_pack2(-m, -m);
         uint64_t l2 = 0ull;
-        float ev[SC];
+        // e = 2^(s - m) in chunks of CH taps, each split into fp16 hi / lo and written back over S right away
+        // (only one chunk of exponentials is ever live; the padded taps cost neither an exp nor a split)
+        constexpr int CH = (SC % 16 == 0) ? 16 : 8;
 #pragma unroll
-        for (int j = 0; j < SC; j += 2) {
-          if (j + 1 < NV) {
-            float d0, d1;
-            tm_unpack2(tm_fma2(tm_pack2(__uint_as_float(mine[j]), __uint_as_float(mine[j + 1])), one2, negm2), d0, d1);
-            ev[j] = fast_exp2(d0);
-            ev[j + 1] = fast_exp2(d1);
-            l2 = tm_fma2(tm_pack2(ev[j], ev[j + 1]), one2, l2);
-          } else if (j < NV) {
-            ev[j] = fast_exp2(__uint_as_float(mine[j]) - m);
-            ev[j + 1] = 0.f;
-            l2 = tm_fma2(tm_pack2(ev[j], 0.f), one2, l2);
+        for (int c0 = 0; c0 < SC; c0 += CH) {
+          uint32_t hi[CH / 2], lo[CH / 2];
+#pragma unroll
+          for (int j = 0; j < CH; j += 2) {
+            const int t = c0 + j;
+            if (t + 1 < NV) {
+              float d0, d1;
+              tm_unpack2(tm_fma2(tm_pack2(__uint_as_float(mine[t]), __uint_as_float(mine[t + 1])), one2, negm2), d0, d1);
+#if NAF_TMA_EXP & 4
+              const float e0 = 1.f + 0.f * d0, e1 = 1.f + 0.f * d1;
+#else
+              const float e0 = fast_exp2(d0), e1 = fast_exp2(d1);
+#endif
+              l2 = tm_fma2(tm_pack2(e0, e1), one2, l2);
+              split2_f16(e0, e1, hi[j / 2], lo[j / 2]);
+            } else if (t < NV) {
+              const float e0 = fast_exp2(__uint_as_float(mine[t]) - m);
+              l2 = tm_fma2(tm_pack2(e0, 0.f), one2, l2);
+              split2_f16(e0, 0.f, hi[j / 2], lo[j / 2]);
+            } else {
+              hi[j / 2] = lo[j / 2] = 0u;
+            }
+          }
+          if constexpr (CH == 16) {
+            tmem_st8(ts + (base + c0) / 2, hi);
+            tmem_st8(ts + TP / 2 + (base + c0) / 2, lo);
           } else {
-            ev[j] = ev[j + 1] = 0.f;
+            tmem_st4(ts + (base + c0) / 2, hi);
+            tmem_st4(ts + TP / 2 + (base + c0) / 2, lo);
           }
         }
         float l0, l1;
         tm_unpack2(l2, l0, l1);
         tmem_st1(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2 + H, __float_as_uint(l0 + l1));
-        if constexpr (SC % 16 == 0) {
-#pragma unroll
-          for (int c0 = 0; c0 < SC; c0 += 16) {
-            uint32_t hi[8], lo[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              if (c0 + 2 * j < NV) split2_f16(ev[c0 + 2 * j], ev[c0 + 2 * j + 1], hi[j], lo[j]);
-              else hi[j] = lo[j] = 0u;
-            }
-            tmem_st8(ts + (base + c0) / 2, hi);
-            tmem_st8(ts + TP / 2 + (base + c0) / 2, lo);
-          }
-        } else {
-#pragma unroll
-          for (int c0 = 0; c0 < SC; c0 += 8) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (c0 + 2 * j < NV) split2_f16(ev[c0 + 2 * j], ev[c0 + 2 * j + 1], hi[j], lo[j]);
-              else hi[j] = lo[j] = 0u;
-            }
-            tmem_st4(ts + (base + c0) / 2, hi);
-            tmem_st4(ts + TP / 2 + (base + c0) / 2, lo);
-          }
-        }
       };
       if (half == 0) softmax_half(std::integral_constant<int, 0>{});
       else softmax_half(std::integral_constant<int, 1>{});
       wait_st();
       fence_before_sync();
       mbar_arrive(&bar_p_full[s]);   // release: l and P (TMEM) are visible to the consumers
+      if constexpr (QS == 1) {
+        if (g + 2 < total_tiles) issue_q();
+      }
     }
   } else if (warp < MMA_WARP) {
     // ======================================================================== BACK (two threads per row)
@@ -417,6 +464,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     }
     int n = 0;      // accumulator uses so far: (tile, half) pairs
     int g = 0;
+    int rc = 0;     // staging rounds so far
     for (int it_seq = 0; it_seq < my_items; ++it_seq) {
       const TmItem it = item_of(it_seq);
       for (int tile = 0; tile < ntiles; ++tile, ++g) {
@@ -433,12 +481,33 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
             wait_ld();
             inv_l = 1.f / (__uint_as_float(l0) + __uint_as_float(l1));
           }
+          // Accumulator halves of <= 128 columns (64 per thread) are pulled into registers in one go and O is
+          // handed back to the tensor core BEFORE the staging rounds: with two halves per tile the next PV
+          // waits for exactly this drain.  Wider accumulators are streamed 16 columns at a time per round.
+          constexpr bool PRELOAD = DVH <= 128;
+          constexpr int PC = PRELOAD ? DVH / 2 : 16;     // columns of this thread held at once
+          uint32_t pre[PC];
+          if constexpr (PRELOAD) {
+            // this thread's columns of round rd: [rd*RC + half*HC, +HC)  ->  pre[rd*HC .. rd*HC+HC)
 #pragma unroll
-          for (int rd = 0; rd < ROUNDS; ++rd) {
+            for (int rd = 0; rd < ROUNDS; ++rd)
+#pragma unroll
+              for (int c = 0; c < HC; c += 16)
+                tmem_ld16(tmem + Cfg::kTmemO + lane_off + rd * RC + half * HC + c,
+                          *reinterpret_cast<uint32_t(*)[16]>(&pre[rd * HC + c]));
+            wait_ld();
+            fence_before_sync();
+            mbar_arrive(&bar_o_free);
+          }
+#pragma unroll
+          for (int rd = 0; rd < ROUNDS; ++rd, ++rc) {
+            // Staging slot of this round.  With two slots nobody waits here: the stores that last read this
+            // slot (round rc-2) were waited for by the issuer before the barrier of round rc-1.
+            uint8_t* const slot = stage_out + (Cfg::NSTG == 2 ? (rc & 1) * Cfg::kSlot : 0);
             const uint32_t to = tmem + Cfg::kTmemO + lane_off + rd * RC + half * HC;
             const uint64_t inv2 = tm_pack2(inv_l, inv_l);
             // normalise 16 accumulator columns and write them into the swizzled box images
-            auto stage16 = [&](const uint32_t (&r)[16], int c) {
+            auto stage16 = [&](const uint32_t* r, int c) {
               if (bf16_out) {
                 // 64 channels per 128-byte box row
 #pragma unroll
@@ -452,7 +521,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
                     pw[e] = *reinterpret_cast<const uint32_t*>(&h2);
                   }
                   const int col = half * HC + c + j;
-                  *reinterpret_cast<uint4*>(stage_out + (col >> 6) * Cfg::kBox + tmap::swz128(row, (col & 63) >> 3)) = pk;
+                  *reinterpret_cast<uint4*>(slot + (col >> 6) * Cfg::kBox + tmap::swz128(row, (col & 63) >> 3)) = pk;
                 }
               } else {
 #pragma unroll
@@ -460,29 +529,15 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
                   const uint64_t o01 = tm_fma2(tm_pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), inv2, 0ull);
                   const uint64_t o23 = tm_fma2(tm_pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), inv2, 0ull);
                   const int col = half * HC + c + j;
-                  *reinterpret_cast<uint4*>(stage_out + (col >> 5) * Cfg::kBox + tmap::swz128(row, (col & 31) >> 2)) =
+                  *reinterpret_cast<uint4*>(slot + (col >> 5) * Cfg::kBox + tmap::swz128(row, (col & 31) >> 2)) =
                       make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
                 }
               }
             };
-            if constexpr (HC <= 32) {
-              // narrow rounds (two accumulator halves per tile): pull the columns into registers first and hand
-              // O back to the tensor core BEFORE waiting for the staging area
-              uint32_t r[HC / 16][16];
+            if constexpr (PRELOAD) {
 #pragma unroll
-              for (int c = 0; c < HC / 16; ++c) tmem_ld16(to + c * 16, r[c]);
-              wait_ld();
-              if (rd == ROUNDS - 1) {
-                fence_before_sync();
-                mbar_arrive(&bar_o_free);
-              }
-              if (issuer) bulk_wait_read<0>();   // the previous round's tensor stores have read the staging area
-              asm volatile("bar.sync 2, 256;" ::: "memory");
-#pragma unroll
-              for (int c = 0; c < HC / 16; ++c) stage16(r[c], c * 16);
+              for (int c = 0; c < HC; c += 16) stage16(&pre[rd * HC + c], c);
             } else {
-              if (issuer) bulk_wait_read<0>();
-              asm volatile("bar.sync 2, 256;" ::: "memory");
               uint32_t r[2][16];
               tmem_ld16(to, r[0]);
 #pragma unroll
@@ -490,7 +545,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
                 wait_ld();
                 if (c + 1 < HC / 16) tmem_ld16(to + (c + 1) * 16, r[(c + 1) & 1]);
                 else if (rd == ROUNDS - 1) {
-                  // the whole accumulator is in registers / staged: the next PV may overwrite O
+                  // the whole accumulator has left TMEM: the next PV may overwrite O
                   fence_before_sync();
                   mbar_arrive(&bar_o_free);
                 }
@@ -498,15 +553,20 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
               }
             }
             fence_proxy_async_smem();
-            asm volatile("bar.sync 3, 256;" ::: "memory");
+            // every store issued so far has read its slot before anybody writes the OTHER slot (next round)
+            if (Cfg::NSTG == 2 && issuer) bulk_wait_read<0>();
+            asm volatile("bar.sync 2, 256;" ::: "memory");
             if (issuer) {
               const CUtensorMap* tm = (last_tile && gm.th_last != gm.th) ? &tmO2 : &tmO;
               const int c0 = it.head * Cfg::DV + hh * DVH + rd * RC;
               const int per_box = bf16_out ? 64 : 32;
               const int nbox = RC / per_box;
-              for (int j = 0; j < nbox; ++j) tmap::store4(tm, c0 + j * per_box, x0, y0, it.b, stage_out + j * Cfg::kBox);
+              if (!(NAF_TMA_EXP & 1))
+                for (int j = 0; j < nbox; ++j) tmap::store4(tm, c0 + j * per_box, x0, y0, it.b, slot + j * Cfg::kBox);
               bulk_commit();
+              if (Cfg::NSTG == 1) bulk_wait_read<0>();
             }
+            if (Cfg::NSTG == 1) asm volatile("bar.sync 3, 256;" ::: "memory");   // single slot: free again
           }
         }
       }
@@ -690,14 +750,21 @@ int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
     ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ws) + 127) & ~uintptr_t(127));
     uint8_t* kplanes = ws;
     uint8_t* vplanes = ws + size_t(p.B) * p.h * p.w * p.D * 4;
-    prefer_max_shared(kv_planes_kernel);
+    prefer_max_shared(kv_planes_kernel<float>);
+    prefer_max_shared(kv_planes_kernel<__nv_bfloat16>);
     {
       const int64_t nk = int64_t(p.B) * (p.D / 8) * p.h * p.w, nv = int64_t(p.B) * (p.C / 8) * p.h * p.w;
       const int64_t cap = int64_t(sms) * 16;
       const int64_t bk_ = (nk + 255) / 256, bv_ = (nv + 255) / 256;
       const unsigned gk_ = unsigned(bk_ < cap ? bk_ : cap), gv_ = unsigned(bv_ < cap ? bv_ : cap);
-      kv_planes_kernel<<<gk_, 256, 0, st>>>(p.k, reinterpret_cast<uint4*>(kplanes), p.B, p.h, p.w, p.D);
-      kv_planes_kernel<<<gv_, 256, 0, st>>>(p.v, reinterpret_cast<uint4*>(vplanes), p.B, p.h, p.w, p.C);
+      if (p.k_dtype == NAF_DTYPE_BF16)
+        kv_planes_kernel<<<gk_, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p.k), reinterpret_cast<uint4*>(kplanes), p.B, p.h, p.w, p.D);
+      else
+        kv_planes_kernel<<<gk_, 256, 0, st>>>(p.k, reinterpret_cast<uint4*>(kplanes), p.B, p.h, p.w, p.D);
+      if (p.v_dtype == NAF_DTYPE_BF16)
+        kv_planes_kernel<<<gv_, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(p.v), reinterpret_cast<uint4*>(vplanes), p.B, p.h, p.w, p.C);
+      else
+        kv_planes_kernel<<<gv_, 256, 0, st>>>(p.v, reinterpret_cast<uint4*>(vplanes), p.B, p.h, p.w, p.C);
       int rc = check_launch("xattn_kv_planes");
       if (rc != NAF_OK) return rc;
     }
@@ -734,41 +801,53 @@ struct TmPlan {
 };
 
 template <int TP>
-constexpr TmPlan tm_plan(int dv) {
-  // whole head in one accumulator when TMEM and shared memory allow, else two halves against one P
+constexpr TmPlan tm_plan(int dv, bool bf16) {
+  // whole head in one accumulator when TMEM allows, else two halves against one P; rounds chosen so that two
+  // staging slots fit (bf16 stores need 64-channel boxes, i.e. rounds of a multiple of 64 columns)
   TmPlan pl;
   switch (dv) {
-    case 32: if (TmaCfg<TP, 32, 1, 1>::kFits) pl = {32, 1, 1}; break;
+    case 32: if (!bf16 && TmaCfg<TP, 32, 1, 1>::kFits) pl = {32, 1, 1}; break;
     case 64: if (TmaCfg<TP, 64, 1, 1>::kFits) pl = {64, 1, 1}; break;
-    case 96: if (TmaCfg<TP, 96, 1, 1>::kFits) pl = {96, 1, 1}; break;
-    case 128: if (TmaCfg<TP, 128, 1, 1>::kFits) pl = {128, 1, 1}; else if (TmaCfg<TP, 64, 2, 1>::kFits) pl = {64, 2, 1}; break;
-    case 192: if (TmaCfg<TP, 192, 1, 1>::kFits) pl = {192, 1, 1}; else if (TmaCfg<TP, 96, 2, 1>::kFits) pl = {96, 2, 1}; break;
-    case 256: if (TmaCfg<TP, 256, 1, 1>::kFits) pl = {256, 1, 1}; else if (TmaCfg<TP, 128, 2, 1>::kFits) pl = {128, 2, 1};
-              else if (TmaCfg<TP, 128, 2, 2>::kFits) pl = {128, 2, 2}; break;
+    case 96: if (!bf16 && TmaCfg<TP, 96, 1, 1>::kFits) pl = {96, 1, 1}; break;
+    case 128: if (TmaCfg<TP, 128, 1, 2>::kFits) pl = {128, 1, 2}; break;
+    case 192:
+      if (bf16) { if (TmaCfg<TP, 192, 1, 1>::kFits) pl = {192, 1, 1}; }
+      else if (TmaCfg<TP, 192, 1, 2>::kFits) pl = {192, 1, 2};
+      break;
+    case 256:
+      if (TmaCfg<TP, 256, 1, 4>::kFits) pl = {256, 1, 4};
+      else if (bf16) { if (TmaCfg<TP, 128, 2, 2>::kFits) pl = {128, 2, 2}; }
+      else if (TmaCfg<TP, 128, 2, 4>::kFits) pl = {128, 2, 4};
+      break;
     default: break;
   }
   return pl;
 }
 
-TmPlan tm_plan_for(int K, int dv) {
+TmPlan tm_plan_for(int K, int dv, bool bf16) {
   switch (tm_taps_pad(K)) {
-    case 16: return tm_plan<16>(dv);
-    case 32: return tm_plan<32>(dv);
-    case 64: return tm_plan<64>(dv);
-    case 96: return tm_plan<96>(dv);
-    case 128: return tm_plan<128>(dv);
+    case 16: return tm_plan<16>(dv, bf16);
+    case 32: return tm_plan<32>(dv, bf16);
+    case 64: return tm_plan<64>(dv, bf16);
+    case 96: return tm_plan<96>(dv, bf16);
+    case 128: return tm_plan<128>(dv, bf16);
     default: return TmPlan{};
   }
 }
 
-template <int TP, int DVFULL>
-int launch_tma_dv(const naf_xattn_params& p, cudaStream_t st) {
-  constexpr TmPlan pl = tm_plan<TP>(DVFULL);
+template <int TP, int DVFULL, bool BF16>
+int launch_tma_plan(const naf_xattn_params& p, cudaStream_t st) {
+  constexpr TmPlan pl = tm_plan<TP>(DVFULL, BF16);
   if constexpr (pl.dvh == 0) {
     return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): no plan for dv=%d", DVFULL);
   } else {
     return launch_tma<TP, pl.dvh, pl.nh, pl.rounds>(p, st);
   }
+}
+
+template <int TP, int DVFULL>
+int launch_tma_dv(const naf_xattn_params& p, cudaStream_t st) {
+  return p.out_dtype == NAF_DTYPE_BF16 ? launch_tma_plan<TP, DVFULL, true>(p, st) : launch_tma_plan<TP, DVFULL, false>(p, st);
 }
 
 template <int TP>
@@ -792,20 +871,24 @@ bool xattn_cell_tma_supported(const naf_xattn_params& p, const char** why) {
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }
-  if (p.scores) { *why = "score output requested"; return false; }
   if (dq != DQ) { *why = "head dim must be 64"; return false; }
   if (p.K < 3 || p.K > 11) { *why = "kernel_size must be 3, 5, 7, 9 or 11"; return false; }
   if (p.h < p.K || p.w < p.K) { *why = "feature map smaller than the window"; return false; }
-  const TmPlan pl = tm_plan_for(p.K, dv);
-  if (!pl.dvh) { *why = "no tile configuration for this window / value head dim"; return false; }
+  const TmPlan pl = tm_plan_for(p.K, dv, p.out_dtype == NAF_DTYPE_BF16);
+  if (!pl.dvh) { *why = "no tile configuration for this window / value head dim / output type"; return false; }
   const int rh = p.Ho / p.h, rw = p.Wo / p.w;
   if (rw > 128) { *why = "cells wider than 128 pixels"; return false; }
   if (rh * rw < 64) { *why = "fewer than 64 pixels per cell"; return false; }
-  if (p.out_dtype == NAF_DTYPE_BF16 && ((pl.dvh / pl.rounds) % 64 || p.C % 8)) { *why = "bf16 store needs 64-channel boxes"; return false; }
+  if (p.out_dtype == NAF_DTYPE_BF16 && p.C % 8) { *why = "bf16 store needs C % 8 == 0"; return false; }
   if (!p.workspace || size_t(p.workspace_bytes) < tm_workspace_bytes(p)) { *why = "workspace missing or too small (naf_xattn_workspace_bytes)"; return false; }
-  if (!aligned32(p.q) || !aligned32(p.k) || !aligned32(p.v) || !aligned16(p.out) || (p.C % 4) ||
-      (p.q_stride_b % 8) || (p.q_stride_y % 8) || (p.q_stride_x % 8)) {
+  const int qa_ = p.q_dtype == NAF_DTYPE_BF16 ? 16 : 8;   // 32-byte aligned query half rows for either element type
+  if (!aligned32(p.q) || !aligned16(p.k) || !aligned16(p.v) || !aligned16(p.out) || (p.C % 8) ||
+      (p.q_stride_b % qa_) || (p.q_stride_y % qa_) || (p.q_stride_x % qa_)) {
     *why = "pointers/strides not aligned";
+    return false;
+  }
+  if ((p.k_dtype == NAF_DTYPE_F32 && !aligned32(p.k)) || (p.v_dtype == NAF_DTYPE_F32 && !aligned32(p.v))) {
+    *why = "fp32 k / v not 32-byte aligned";
     return false;
   }
   if (p.cos_y && !(aligned32(p.cos_y) && aligned32(p.sin_y) && aligned32(p.cos_x) && aligned32(p.sin_x))) {
@@ -814,7 +897,6 @@ bool xattn_cell_tma_supported(const naf_xattn_params& p, const char** why) {
   }
   if (int64_t(p.B) * p.h * p.w * p.heads >= (int64_t(1) << 31)) { *why = "too many items"; return false; }
   if (int64_t(p.B) * 2 * (p.C / 8) >= (int64_t(1) << 31)) { *why = "too many planes"; return false; }
-  if (!tmap::encode_fn()) { *why = "cuTensorMapEncodeTiled not available from the driver"; return false; }
   return true;
 }
 

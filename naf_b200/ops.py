@@ -223,7 +223,19 @@ def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo
     p.algo = int(algo)
     p.rep_y, p.rep_x = int(rep[0]), int(rep[1])
     p.out_dtype = _lib.DTYPE_BF16 if out.dtype == torch.bfloat16 else _lib.DTYPE_F32
+    p.q_dtype, p.k_dtype, p.v_dtype = (_lib.DTYPE_BF16 if t.dtype == torch.bfloat16 else _lib.DTYPE_F32 for t in (q, k, v))
     return p
+
+
+def _native_pixel_major(t: torch.Tensor, contiguous: bool) -> torch.Tensor:
+    """bf16 tensor as an NCHW-shaped view of pixel-major storage WITHOUT widening it (layout changes, when
+    needed at all, are torch's channels_last copy of the bf16 data: plumbing on the small maps)."""
+    sb, sc, sy, sx = t.stride()
+    Cn = t.shape[1]
+    ok = (Cn == 1 or sc == 1) and sx >= Cn and sx % 16 == 0 and sy % 16 == 0 and sb % 16 == 0 and t.data_ptr() % 32 == 0
+    if ok and (not contiguous or t.permute(0, 2, 3, 1).is_contiguous()):
+        return t
+    return t.contiguous(memory_format=torch.channels_last)
 
 
 def _launch_xattn(p, dev) -> None:
@@ -262,20 +274,29 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_
     if scale is None:
         scale = (D // heads) ** -0.5
     tap_tabs = device_tap_tables(Ho, Wo, h, w, K, dev)  # validates the window too
-    q = as_pixel_major(q)
-    k = as_pixel_major(k)
-    v = as_pixel_major(v)
-    # k and v must be fully contiguous pixel-major
-    if not k.permute(0, 2, 3, 1).is_contiguous():
-        k = pack_nhwc(k).permute(0, 3, 1, 2)
-    if not v.permute(0, 2, 3, 1).is_contiguous():
-        v = pack_nhwc(v).permute(0, 3, 1, 2)
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise NotImplementedError(f"xattn: out_dtype {out_dtype} (float32 or bfloat16)")
     out = torch.empty((B, Ho, Wo, Cn), device=dev, dtype=out_dtype)
     scores = (torch.empty((B, heads, Ho, Wo, K * K), device=dev, dtype=torch.float32)
               if return_scores else None)
-    p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo, rep)
+    p = None
+    if any(t.dtype == torch.bfloat16 for t in (q, k, v)) and algo in (_lib.ALGO_AUTO, _lib.ALGO_CELL_TMA):
+        # bf16 inputs (the reference under autocast, train.py:120): the TMA kernel reads them as they are
+        qn, kn, vn = (_native_pixel_major(t, c) if t.dtype == torch.bfloat16 else None
+                      for t, c in ((q, False), (k, True), (v, True)))
+        qn = qn if qn is not None else as_pixel_major(q)
+        kn = kn if kn is not None else _contig_pixel_major(k)
+        vn = vn if vn is not None else _contig_pixel_major(v)
+        pn = _fill_xattn(qn, kn, vn, out, scores, heads, K, scale, tap_tabs, rope_tables, algo, rep)
+        pn.workspace, pn.workspace_bytes = 256, 1 << 62      # "if it had its workspace"
+        if _lib.load().naf_xattn_select_algo(C.byref(pn)) == _lib.ALGO_CELL_TMA:
+            pn.workspace, pn.workspace_bytes = 0, 0
+            p, q, k, v = pn, qn, kn, vn
+    if p is None:
+        q = as_pixel_major(q)           # (widens anything that is not fp32)
+        k = _contig_pixel_major(k)      # k and v must be fully contiguous pixel-major
+        v = _contig_pixel_major(v)
+        p = _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tables, algo, rep)
     # scratch for the TMA kernel's fp16 K / V planes (the C side never allocates); freed to the caching
     # allocator when this function returns -- stream-ordered, so the enqueued kernels still own it
     ws_bytes = int(_lib.load().naf_xattn_workspace_bytes(C.byref(p)))

@@ -3,7 +3,7 @@
 tag=${1:-ab}; shift
 out=gpurun_out/$tag
 mkdir -p $out
-( timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tma.py -m gpu -q --tb=short -x "$@" 2>&1 | tail -150 ) > $out/pytest.log
+( timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tma.py -m gpu -q --tb=short -x "$@" 2>&1 | tail -150 ) > $out/pytest.log
 tail -4 $out/pytest.log
 {
 for algo in cell_tcws cell_tma; do

@@ -65,7 +65,8 @@ def test_kernel_selection_for_baseline_configs():
     assert sel((2, 256, 1344, 1344), (2, 768, 24, 24), 4, 7) in fast    # C4
     assert sel((4, 256, 2048, 2048), (4, 768, 32, 32), 4, 7) in fast    # C5
     assert sel((1, 64, 32, 32), (1, 16, 13, 13), 4, 9) == "generic"     # non-integer ratio
-    assert sel((1, 256, 36, 36), (1, 32, 9, 9), 4, 7, return_scores=True) == "generic"
+    assert sel((1, 256, 36, 36), (1, 32, 9, 9), 4, 7, return_scores=True) == "generic"      # 16-pixel cells
+    assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7, return_scores=True) == "cell_tma"  # scores on the fast kernel
 
 
 def test_validation_errors_map_to_reference_exceptions():
