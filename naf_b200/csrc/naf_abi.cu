@@ -154,8 +154,21 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
   }
   if (p.algo != NAF_ALGO_AUTO) return -fail(NAF_ERR_UNSUPPORTED, "xattn: unknown algo %d", p.algo);
   (void)explain;
-  if (xattn_cell_tma_supported(p, &why)) return NAF_ALGO_CELL_TMA;
-  if (xattn_cell_tcws_supported(p, &why)) return NAF_ALGO_CELL_TCWS;
+  const bool tma_ok = xattn_cell_tma_supported(p, &why);
+  const bool ws_ok = xattn_cell_tcws_supported(p, &why);
+  if (tma_ok && ws_ok) {
+    // Both pipelined tensor-core kernels take the request: measured choice (profiles/).  The TMA
+    // kernel wins where windows turn over quickly and for wide value heads (C2 4.41 vs 4.62 ms, C3 5.8 vs 8.5 ms);
+    // the in-kernel-conversion kernel keeps 2-5 % on very large cells, where a window serves >= 16 tiles and its
+    // per-thread bulk-copy epilogue streams better (C4 2.11 vs 2.17 ms, C5 10.6 vs 11.1 ms), and on latency-bound
+    // launches that cannot amortise the plane pre-pass (C1: 0.067 vs 0.078 ms).
+    const int64_t cell_px = int64_t(p.Ho / p.h) * (p.Wo / p.w);
+    const int64_t items = int64_t(p.B) * p.h * p.w * p.heads;
+    if (cell_px >= 2048 || items < 2048) return NAF_ALGO_CELL_TCWS;
+    return NAF_ALGO_CELL_TMA;
+  }
+  if (tma_ok) return NAF_ALGO_CELL_TMA;
+  if (ws_ok) return NAF_ALGO_CELL_TCWS;
   if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
   return NAF_ALGO_GENERIC;
 }

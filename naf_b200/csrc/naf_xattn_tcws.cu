@@ -809,6 +809,7 @@ bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why) {
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }
   if (p.scores) { *why = "score output requested"; return false; }
+  if (p.q_dtype != NAF_DTYPE_F32 || p.k_dtype != NAF_DTYPE_F32 || p.v_dtype != NAF_DTYPE_F32) { *why = "fp32 inputs only"; return false; }
   if (NAF_WS_EPI && p.out_dtype != NAF_DTYPE_F32) { *why = "fp32 output only in this build"; return false; }
   if (dq != DQ) { *why = "head dim must be 64"; return false; }
   if (p.K < 3) { *why = "kernel_size must be 3, 5, 7, 9 or 11"; return false; }

@@ -48,7 +48,7 @@ constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 64;
 constexpr int MMA_WARP = (NFRONT + NBACK) / 32, LOAD_WARP = MMA_WARP + 1;
 #ifndef NAF_TMA_EXP
 #define NAF_TMA_EXP 0   // profiling variants (scripts/build_variant.py): 1 = no output stores, 2 = no q loads,
-#endif                  // 4 = softmax without the exponentials (P = 1 on the valid taps)
+#endif                  // 4 = softmax without the exponentials (P = 1 on the valid taps), 8 = constant cos/sin (no table loads)
 constexpr int kSmemLimit = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (static barriers extra)
 
 template <int TP>
@@ -73,7 +73,8 @@ struct TmaCfg {
   static constexpr int kBox = 128 * 128;                        // one staging box image: 128 rows x 128 B
   static constexpr int kSlot = (kRoundCols / 32) * kBox;        // one staging slot: a round's boxes (fp32: 32 channels per
                                                                 // box; bf16: 64, half the boxes)
-  static constexpr int kMx = 2 * 2 * 128 * 4;                   // row-max exchange between the two row halves
+  static constexpr int kMx = (2 * 2 + 4 * 2) * 128 * 4;         // row-max exchange between the two row halves [2][2][128]
+                                                                // + softmax row sums for the epilogue [4][2][128]
   static constexpr int NKB = 2;
   static constexpr int kMin = NKB * kKWin + kVWin + kSlot + kMx + 1024;   // one V buffer, one staging slot
   // what is left goes first to a second staging slot (the tensor stores of round r read slot r&1 while round
@@ -86,12 +87,13 @@ struct TmaCfg {
   static constexpr int kOffStage = round_up(kOffV + NVB * kVWin, 1024);
   static constexpr int kOffMx = kOffStage + kStage;
   static constexpr int kSmemBytes = kOffMx + kMx;
-  static constexpr int kQStages = (128 + 2 * TP + DVH + 8 <= 512) ? 2 : 1;
+  // (the row sums travel through shared memory, not TMEM: 128 + 2*128 + 128 columns is exactly 512, which gives
+  // the 11x11 / dv 256 configuration its second Q stage)
+  static constexpr int kQStages = (128 + 2 * TP + DVH <= 512) ? 2 : 1;
   static constexpr int kTmemQ = 0;
   static constexpr int kTmemS = 64 * kQStages;
   static constexpr int kTmemO = kTmemS + 2 * TP;
-  static constexpr int kTmemL = kTmemO + DVH;
-  static constexpr int kTmemUsed = kTmemL + 8;
+  static constexpr int kTmemUsed = kTmemO + DVH;
   static constexpr bool kFits = kTmemUsed <= 512 && kSmemBytes <= kSmemLimit && (DVH % ROUNDS) == 0 &&
                                 (kRoundCols % 32) == 0 && DVH % 16 == 0 && DVH <= 256 && DV / 8 <= 256;
 };
@@ -205,6 +207,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
   uint8_t* const sV = smem + Cfg::kOffV;
   uint8_t* const stage_out = smem + Cfg::kOffStage;
   float* const mx = reinterpret_cast<float*>(smem + Cfg::kOffMx);   // [tile parity][half][row]
+  float* const lsum = mx + 2 * 2 * 128;                             // [tile & 3][half][row]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rh = gm.rh, rw = gm.rw;
@@ -302,10 +305,16 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         const float* ct = half == 0 ? p.cos_y + int64_t(q_y) * P : p.cos_x + int64_t(q_x) * P;
         const float* st = half == 0 ? p.sin_y + int64_t(q_y) * P : p.sin_x + int64_t(q_x) * P;
         float c[P], sn[P];
+#if NAF_TMA_EXP & 8
+#pragma unroll
+        for (int j = 0; j < P; ++j) { c[j] = 0.8f; sn[j] = 0.6f; }
+        (void)ct; (void)st;
+#else
         ldg8(ct, *reinterpret_cast<float(*)[8]>(&c[0]));
         ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
         ldg8(st, *reinterpret_cast<float(*)[8]>(&sn[0]));
         ldg8(st + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+#endif
         const uint64_t qs2 = tm_pack2(qscale, qscale);
 #pragma unroll
         for (int j = 0; j < P; j += 2) {
@@ -345,19 +354,20 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     }
     for (int g = 0; g < total_tiles; ++g) {
       const int s = g & 1;
+      // With one Q stage the prefetch of tile g+2 is issued after the softmax (its consumer, stage_q(g+2), comes
+      // after the wait for S(g+1)).  With two stages stage_q(g+2) opens the next iteration, so the loads must be
+      // in flight across the softmax (measured: issuing them late exposes the whole load latency once per tile).
+      constexpr bool LATE_Q = QS == 1;
       if constexpr (QS == 2) {
         if (g + 1 < total_tiles) {
           stage_q(g + 1);
-          if (g + 2 < total_tiles) issue_q();
+          if (!LATE_Q && g + 2 < total_tiles) issue_q();
         }
       }
       mbar_wait(&bar_s_full[s], (g >> 1) & 1);
       fence_after_sync();
       if constexpr (QS == 1) {
-        // one Q stage (128-tap windows): the prefetch of tile g+2 is issued AFTER the softmax below, so that the
-        // 32 query registers are not live across it (the 64-value softmax rows need the registers; the loads
-        // still have QK(g+1) plus the wait for it to complete)
-        if (g + 1 < total_tiles) stage_q(g + 1);
+        if (g + 1 < total_tiles) stage_q(g + 1);   // one Q stage: QK(g) must have read it first
       }
       const uint32_t ts = tmem + Cfg::kTmemS + s * TP + lane_off;
       auto softmax_half = [&](auto half_c) {
@@ -437,14 +447,16 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         }
         float l0, l1;
         tm_unpack2(l2, l0, l1);
-        tmem_st1(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2 + H, __float_as_uint(l0 + l1));
+        // row sum for the epilogue, slot [tile & 3][half] (the epilogue may lag two tiles behind); published by
+        // the release of the p_full arrive below, observed through the MMA thread's commit to o_full
+        lsum[((g & 3) * 2 + H) * 128 + row] = l0 + l1;
       };
       if (half == 0) softmax_half(std::integral_constant<int, 0>{});
       else softmax_half(std::integral_constant<int, 1>{});
       wait_st();
       fence_before_sync();
       mbar_arrive(&bar_p_full[s]);   // release: l and P (TMEM) are visible to the consumers
-      if constexpr (QS == 1) {
+      if constexpr (LATE_Q) {
         if (g + 2 < total_tiles) issue_q();
       }
     }
@@ -476,10 +488,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
           mbar_wait(&bar_o_full, n & 1);
           fence_after_sync();
           if (hh == 0) {
-            uint32_t l0, l1;
-            tmem_ld2(tmem + Cfg::kTmemL + lane_off + (g & 3) * 2, l0, l1);
-            wait_ld();
-            inv_l = 1.f / (__uint_as_float(l0) + __uint_as_float(l1));
+            inv_l = 1.f / (lsum[((g & 3) * 2) * 128 + row] + lsum[((g & 3) * 2 + 1) * 128 + row]);
           }
           // Accumulator halves of <= 128 columns (64 per thread) are pulled into registers in one go and O is
           // handed back to the tensor core BEFORE the staging rounds: with two halves per tile the next PV

@@ -58,12 +58,11 @@ int main(void){
 
 def test_kernel_selection_for_baseline_configs():
     sel = ops.select_algo
-    fast = {"cell_simt", "cell_tcws", "cell_tma"}
-    assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7) in fast      # C1
-    assert sel((8, 256, 896, 896), (8, 768, 32, 32), 4, 7) in fast      # C2
-    assert sel((4, 256, 1036, 1036), (4, 1024, 37, 37), 4, 11) in fast  # C3
-    assert sel((2, 256, 1344, 1344), (2, 768, 24, 24), 4, 7) in fast    # C4
-    assert sel((4, 256, 2048, 2048), (4, 768, 32, 32), 4, 7) in fast    # C5
+    assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7) == "cell_tcws"      # C1: latency bound, no pre-pass
+    assert sel((8, 256, 896, 896), (8, 768, 32, 32), 4, 7) == "cell_tma"       # C2
+    assert sel((4, 256, 1036, 1036), (4, 1024, 37, 37), 4, 11) == "cell_tma"   # C3: single-pass wide heads
+    assert sel((16, 256, 1344, 1344), (16, 768, 24, 24), 4, 7) == "cell_tcws"  # C4: 56x56-pixel cells
+    assert sel((4, 256, 2048, 2048), (4, 768, 32, 32), 4, 7) == "cell_tcws"    # C5: 64x64-pixel cells
     assert sel((1, 64, 32, 32), (1, 16, 13, 13), 4, 9) == "generic"     # non-integer ratio
     assert sel((1, 256, 36, 36), (1, 32, 9, 9), 4, 7, return_scores=True) == "generic"      # 16-pixel cells
     assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7, return_scores=True) == "cell_tma"  # scores on the fast kernel
