@@ -157,7 +157,7 @@ typedef struct naf_xattn_params {
   int32_t reserved_;
 } naf_xattn_params;
 
-enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1 };
+enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1, NAF_DTYPE_F16 = 2 /* encoder activations only */ };
 
 enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2,
        NAF_ALGO_CELL_TC = 3 /* removed in ABI v3 (non-pipelined tensor-core kernel); requests fail with NAF_ERR_UNSUPPORTED */,
@@ -295,6 +295,18 @@ NAF_API int naf_enc_conv_pack_f32(const float* weight, void* packed, int KS, voi
 NAF_API int naf_enc_conv_f32(const float* in, const float* coef, const void* wpacked, const float* bias,
                              float* out, int64_t out_pix_stride, int out_channel_offset, float* part,
                              int B, int H, int W, int KS, int passes, void* stream);
+
+/* The same three entry points with the element type of the ACTIVATIONS between the layers made explicit
+ * (NAF_DTYPE_F32 or NAF_DTYPE_F16).  fp16 activations are part of the 1-pass (TF32) class only: that class
+ * rounds the convolution's input operand to fp16 anyway, so storing the previous layer's output as fp16
+ * halves the HBM bytes of every layer; GroupNorm statistics are still taken from the fp32 accumulators.
+ * `tensor_core` selects naf_enc_stem_tc_f32's GEMM stem (1) or naf_enc_stem_f32's SIMT stem (0). */
+NAF_API int naf_enc_stem_ex(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
+                            int64_t stride_w, const float* weight, const float* bias, void* out, float* part,
+                            int B, int H, int W, int KS, int tensor_core, int out_dtype, void* stream);
+NAF_API int naf_enc_conv_ex(const void* in, const float* coef, const void* wpacked, const float* bias, void* out,
+                            int64_t out_pix_stride, int out_channel_offset, float* part, int B, int H, int W,
+                            int KS, int passes, int in_dtype, int out_dtype, void* stream);
 
 #ifdef __cplusplus
 }

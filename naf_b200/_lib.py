@@ -91,7 +91,7 @@ class KPoolBwdParams(C.Structure):
     ]
 
 
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 
 #: every symbol include/naf_b200.h declares: name -> (restype, argtypes)
 EXPORTS = {
@@ -121,6 +121,10 @@ EXPORTS = {
     "naf_enc_conv_pack_f32": (C.c_int, [_fp, _fp, C.c_int, _fp]),
     "naf_enc_conv_f32": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, C.c_int, C.c_int,
                                    C.c_int, C.c_int, C.c_int, _fp]),
+    "naf_enc_stem_ex": (C.c_int, [_fp, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _fp, _fp, _fp, _fp,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
+    "naf_enc_conv_ex": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, C.c_int, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _fp]),
     "naf_xattn_dump_taps_i32": (C.c_int, [_fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_int, _fp]),
 }

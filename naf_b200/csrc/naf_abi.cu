@@ -340,7 +340,7 @@ int naf_enc_stem_f32(const float* image, int64_t stride_b, int64_t stride_c, int
   NAF_REQUIRE(image && weight && out, NAF_ERR_NULL, "enc_stem: NULL pointer");
   NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_stem: sizes must be positive");
   return launch_enc_stem(image, stride_b, stride_c, stride_h, stride_w, weight, bias, out, part, B, H, W,
-                         KS, static_cast<cudaStream_t>(stream));
+                         KS, NAF_DTYPE_F32, static_cast<cudaStream_t>(stream));
 }
 
 int naf_enc_stem_tc_f32(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h,
@@ -352,7 +352,7 @@ int naf_enc_stem_tc_f32(const float* image, int64_t stride_b, int64_t stride_c, 
   return fail(NAF_ERR_UNSUPPORTED, "enc_stem_tc: library built without the tensor-core path");
 #else
   return launch_enc_stem_tc(image, stride_b, stride_c, stride_h, stride_w, weight, bias, out, part, B, H, W,
-                            KS, static_cast<cudaStream_t>(stream));
+                            KS, NAF_DTYPE_F32, static_cast<cudaStream_t>(stream));
 #endif
 }
 
@@ -377,7 +377,33 @@ int naf_enc_conv_f32(const float* in, const float* coef, const void* wpacked, co
   return fail(NAF_ERR_UNSUPPORTED, "enc_conv: library built without the tensor-core path");
 #else
   return launch_enc_conv(in, coef, wpacked, bias, out, out_pix_stride, out_channel_offset, part, B, H, W,
-                         KS, passes, static_cast<cudaStream_t>(stream));
+                         KS, passes, NAF_DTYPE_F32, NAF_DTYPE_F32, static_cast<cudaStream_t>(stream));
+#endif
+}
+
+int naf_enc_stem_ex(const float* image, int64_t stride_b, int64_t stride_c, int64_t stride_h, int64_t stride_w,
+                    const float* weight, const float* bias, void* out, float* part, int B, int H, int W, int KS,
+                    int tensor_core, int out_dtype, void* stream) {
+  NAF_REQUIRE(image && weight && out, NAF_ERR_NULL, "enc_stem_ex: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_stem_ex: sizes must be positive");
+#ifndef NAF_WITH_TC
+  if (tensor_core) return fail(NAF_ERR_UNSUPPORTED, "enc_stem_ex: library built without the tensor-core path");
+#endif
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return tensor_core ? launch_enc_stem_tc(image, stride_b, stride_c, stride_h, stride_w, weight, bias, out, part, B, H, W, KS, out_dtype, st)
+                     : launch_enc_stem(image, stride_b, stride_c, stride_h, stride_w, weight, bias, out, part, B, H, W, KS, out_dtype, st);
+}
+
+int naf_enc_conv_ex(const void* in, const float* coef, const void* wpacked, const float* bias, void* out,
+                    int64_t out_pix_stride, int out_channel_offset, float* part, int B, int H, int W, int KS,
+                    int passes, int in_dtype, int out_dtype, void* stream) {
+  NAF_REQUIRE(in && coef && wpacked && out, NAF_ERR_NULL, "enc_conv_ex: NULL pointer");
+  NAF_REQUIRE(B > 0 && H > 0 && W > 0, NAF_ERR_BAD_SHAPE, "enc_conv_ex: sizes must be positive");
+#ifndef NAF_WITH_TC
+  return fail(NAF_ERR_UNSUPPORTED, "enc_conv_ex: library built without the tensor-core path");
+#else
+  return launch_enc_conv(in, coef, wpacked, bias, out, out_pix_stride, out_channel_offset, part, B, H, W, KS, passes,
+                         in_dtype, out_dtype, static_cast<cudaStream_t>(stream));
 #endif
 }
 

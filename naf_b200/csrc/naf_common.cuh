@@ -152,13 +152,15 @@ int launch_gn_stats(const float* y, const float* bias, double* sums, int B, int6
 int launch_gn_silu_apply(const float* y, const float* bias, const float* gamma, const float* beta,
                          const double* sums, float* out, int B, int H, int W, int C, int G, float eps,
                          int pad, cudaStream_t st);
-int launch_enc_conv(const float* in, const float* coef, const void* wpack, const float* bias, float* out,
+int launch_enc_conv(const void* in, const float* coef, const void* wpack, const float* bias, void* out,
                     int64_t out_pix_stride, int out_ch_off, float* part, int B, int H, int W, int KS,
-                    int passes, cudaStream_t st);
+                    int passes, int in_dtype, int out_dtype, cudaStream_t st);
 int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
-                    const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st);
+                    const float* bias, void* out, float* part, int B, int H, int W, int KS, int out_dtype,
+                    cudaStream_t st);
 int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
-                       const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st);
+                       const float* bias, void* out, float* part, int B, int H, int W, int KS, int out_dtype,
+                       cudaStream_t st);
 int launch_enc_gn_coef(const float* part, const float* gamma, const float* beta, float* coef, int B, int H,
                        int W, float eps, cudaStream_t st);
 int launch_enc_conv_pack(const float* w, void* packed, int KS, cudaStream_t st);

@@ -70,12 +70,16 @@ struct ConvCfg {
   static constexpr int CTAS_PER_SM = PASSES == 1 ? 2 : 1;
 };
 
+// Activation element type between the layers: fp32, or -- TF32 class only -- fp16 (`IN16` / `OUT16` template
+// flags): the 1-pass kernels round their A operand to fp16 anyway, so storing the conv output as fp16 halves
+// the HBM bytes of every layer and the load instructions / in-flight registers of the producers.  GroupNorm
+// statistics are always taken from the fp32 accumulators.
 struct ConvParams {
-  const float* in;        // (B,H,W,128) contiguous
+  const void* in;         // (B,H,W,128) contiguous, fp32 or fp16
   const float2* coef;     // (B,128) {scale, shift} of the GroupNorm applied to `in`
   const uint8_t* wpack;   // [tap][plane hi|lo][chunk 16][n 128][8 x fp16]
   const float* bias;      // (128) or NULL
-  float* out;             // pixel-major, out_pix_stride floats per pixel, channels [out_ch_off, +128)
+  void* out;              // pixel-major, out_pix_stride elements per pixel, channels [out_ch_off, +128); fp32 or fp16
   float* part;            // NULL or (B, tiles_y*tiles_x, 8 groups, {sum, sumsq})
   int64_t out_pix_stride;
   int out_ch_off;
@@ -218,7 +222,7 @@ conv128_tc_kernel(ConvParams p) {
         sc[j] = c.x;
         sh[j] = c.y;
       }
-      const float* img = p.in + int64_t(b) * p.H * p.W * CC + chunk * 8;
+      const float* img = static_cast<const float*>(p.in) + int64_t(b) * p.H * p.W * CC + chunk * 8;
 #pragma unroll 4
       for (int px = px0; px < HP; px += 16) {
         const int hy = px / WX, hx = px - hy * WX;
@@ -266,7 +270,7 @@ conv128_tc_kernel(ConvParams p) {
       const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
       const int sub = lane >> 3, piece = lane & 7;
       const int ybase = y0 + (warp & 3) * 4, xbase = x0 + sub;
-      float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off +
+      float* obase = static_cast<float*>(p.out) + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off +
                      hf * 64 + piece * 4;
       float st[8];
 #pragma unroll
@@ -384,6 +388,7 @@ conv128_tc_kernel(ConvParams p) {
 // Epilogue of one 16x8 tile for the pipelined kernels (4 warps, warp ew owns TMEM lanes = pixels
 // [32 ew, 32 ew + 32)): accumulator -> +bias -> GroupNorm partial sums -> per-warp transpose slab ->
 // stores of four 128-byte runs per instruction.  `tmem_acc` = accumulator base + this warp's lane offset.
+template <bool OUT16>
 __device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem_acc, uint64_t* bar_acc_free, int b,
                                               int y0, int x0, int tile, int ew, int lane, int et, uint8_t* my_stage,
                                               const uint8_t* warp_stage, const float* s_bias, float (*s_part)[16]) {
@@ -392,7 +397,9 @@ __device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem
   const uint64_t one2 = pack2(1.f, 1.f);
   const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
   const int ybase = y0 + ew * 4, xbase = x0 + sub;
-  float* obase = p.out + ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off + piece * 4;
+  const int64_t oelem = ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off + piece * 4;
+  float* obase = static_cast<float*>(p.out) + oelem;          // fp32 view
+  __half* obase_h = static_cast<__half*>(p.out) + oelem;      // fp16 view (OUT16)
   uint64_t st2[16];   // [group][sum | sumsq], each as an (even, odd) channel pair
 #pragma unroll
   for (int j = 0; j < 16; ++j) st2[j] = 0ull;
@@ -416,16 +423,32 @@ __device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem
       st2[g * 2] = fma2(o23, one2, st2[g * 2]);
       st2[g * 2 + 1] = fma2(o01, o01, st2[g * 2 + 1]);
       st2[g * 2 + 1] = fma2(o23, o23, st2[g * 2 + 1]);
-      *reinterpret_cast<uint4*>(my_stage + j * 4) =
-          make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
+      if constexpr (OUT16) {
+        float a0, a1, a2, a3;
+        unpack2(o01, a0, a1);
+        unpack2(o23, a2, a3);
+        const __half2 h01 = __floats2half2_rn(a0, a1), h23 = __floats2half2_rn(a2, a3);
+        *reinterpret_cast<uint2*>(my_stage + j * 2) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+      } else {
+        *reinterpret_cast<uint4*>(my_stage + j * 4) =
+            make_uint4(uint32_t(o01), uint32_t(o01 >> 32), uint32_t(o23), uint32_t(o23 >> 32));
+      }
     }
     __syncwarp();
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float4 o = *reinterpret_cast<const float4*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 16);
       const int yy = ybase + (i >> 1), xx = xbase + (i & 1) * 4;
-      if (yy < p.H && xx < p.W && !(NAF_CONV_EXP & 1))
-        stg_stream(obase + (int64_t(i >> 1) * p.W + (i & 1) * 4) * p.out_pix_stride + rd * 32, o);
+      const bool ok = yy < p.H && xx < p.W && !(NAF_CONV_EXP & 1);
+      const int64_t off = (int64_t(i >> 1) * p.W + (i & 1) * 4) * p.out_pix_stride + rd * 32;
+      if constexpr (OUT16) {
+        // 32 fp16 channels = 64 bytes per pixel and round: four 64-byte runs per store instruction
+        const uint2 o = *reinterpret_cast<const uint2*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 8);
+        if (ok) asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(obase_h + off), "r"(o.x), "r"(o.y) : "memory");
+      } else {
+        const float4 o = *reinterpret_cast<const float4*>(warp_stage + (i * 4 + sub) * STAGE_SLOT + piece * 16);
+        if (ok) stg_stream(obase + off, o);
+      }
     }
   }
   if (p.part) {
@@ -482,17 +505,19 @@ struct WsConvCfg {
 };
 
 struct TileCtx {
-  const float* img;   // image base + this thread's channel chunk
-  const float* org;   // halo origin of the tile (dereferenced only when interior)
+  const uint8_t* img;   // image base + this thread's channel chunk (bytes)
+  const uint8_t* org;   // halo origin of the tile (dereferenced only when interior)
   int b, y0, x0;
   bool interior, valid;
 };
 }  // namespace
 
-template <int KS>
+template <int KS, bool IN16, bool OUT16>
 __global__ void __launch_bounds__(WS_THREADS, 1)
 conv128_ws_kernel(ConvParams p) {
   using Cfg = ConvCfg<KS, 1>;
+  constexpr int ES = IN16 ? 2 : 4;              // bytes per input activation element
+  const uint8_t* const in_b = static_cast<const uint8_t*>(p.in);
   using Ws = WsConvCfg<KS>;
   constexpr int WX = Cfg::WX, HP = Cfg::HP, CS = Cfg::CS, NT = Cfg::NT;
   constexpr int BS = Ws::BS, NB = Ws::NB;
@@ -541,29 +566,30 @@ conv128_ws_kernel(ConvParams p) {
     auto ctx_of = [&](int tile) {
       TileCtx c;
       c.valid = tile < total;
-      c.b = 0; c.y0 = 0; c.x0 = 0; c.interior = false; c.img = p.in; c.org = p.in;
+      c.b = 0; c.y0 = 0; c.x0 = 0; c.interior = false; c.img = in_b; c.org = in_b;
       if (c.valid) {
         c.b = tile / tiles_per_img;
         const int rem = tile - c.b * tiles_per_img, ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         c.y0 = ty * TH;
         c.x0 = tx * TW;
         c.interior = c.y0 >= KS / 2 && c.y0 + TH + KS / 2 <= p.H && c.x0 >= KS / 2 && c.x0 + TW + KS / 2 <= p.W;
-        c.img = p.in + int64_t(c.b) * p.H * p.W * CC + chunk * 8;
-        c.org = c.img + (int64_t(c.y0 - KS / 2) * p.W + (c.x0 - KS / 2)) * CC;
+        c.img = in_b + (int64_t(c.b) * p.H * p.W * CC + chunk * 8) * ES;
+        c.org = c.img + (int64_t(c.y0 - KS / 2) * p.W + (c.x0 - KS / 2)) * CC * ES;
       }
       return c;
     };
     auto load_batch = [&](const TileCtx& c, int j, float (&v)[BS][8]) {
+      static_assert(NAF_CONV_ITEMPIPE || !IN16, "the batched producer variant reads fp32 activations only");
 #pragma unroll
       for (int kk = 0; kk < BS; ++kk) {
         const int px = px0 + WS_PXS * (j * BS + kk);
         if (HP % WS_PXS == 0 || px < HP) {
           const float* src;
           if (c.interior) {
-            src = c.org + s_goff[px];
+            src = reinterpret_cast<const float*>(c.org) + s_goff[px];
           } else {
             const int hy = px / WX, hx = px - hy * WX;
-            src = c.img + (int64_t(reflect_clamp(c.y0 + hy - KS / 2, p.H)) * p.W +
+            src = reinterpret_cast<const float*>(c.img) + (int64_t(reflect_clamp(c.y0 + hy - KS / 2, p.H)) * p.W +
                            reflect_clamp(c.x0 + hx - KS / 2, p.W)) * CC;
           }
 #if NAF_CONV_EXP & 2
@@ -598,29 +624,48 @@ conv128_ws_kernel(ConvParams p) {
     // Per-item software pipeline of depth DEPTH = NIT / 2: item k is converted DEPTH items after its load
     // was issued (the batched variant gives a load only one batch of conversions to land, less than an L2
     // hit takes); the register budget is the same DEPTH x 8 floats.
-    constexpr int NIT = Ws::NIT, DEPTH = NIT / 2;
+    // fp16 activations: an item is 4 registers instead of 8, so the same register budget holds the loads of
+    // a WHOLE tile (item k of the next tile is issued as soon as item k of this one has been converted)
+    constexpr int NIT = Ws::NIT, DEPTH = IN16 ? NIT : NIT / 2;
+    constexpr int IW = IN16 ? 4 : 8;             // 32-bit registers per item (8 channels)
     static_assert(NIT % DEPTH == 0, "item pipeline");
-    float v[DEPTH][8];
-    auto load_item = [&](const TileCtx& c, int k, float (&dst)[8]) {
+    uint32_t v[DEPTH][IW];
+    auto load_item = [&](const TileCtx& c, int k, uint32_t (&dst)[IW]) {
       const int px = px0 + WS_PXS * k;
       if (HP % WS_PXS == 0 || px < HP) {
-        const float* src;
+        const uint8_t* src;
         if (c.interior) {
-          src = c.org + s_goff[px];
+          src = c.org + int64_t(s_goff[px]) * ES;
         } else {
           const int hy = px / WX, hx = px - hy * WX;
           src = c.img + (int64_t(reflect_clamp(c.y0 + hy - KS / 2, p.H)) * p.W +
-                         reflect_clamp(c.x0 + hx - KS / 2, p.W)) * CC;
+                         reflect_clamp(c.x0 + hx - KS / 2, p.W)) * CC * ES;
         }
-        ldg_stream8(src, dst);
+        if constexpr (IN16) {
+          asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+              : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]) : "l"(src));
+        } else {
+          asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+              : "=r"(dst[0]), "=r"(dst[1]), "=r"(dst[2]), "=r"(dst[3]), "=r"(dst[4]), "=r"(dst[5]), "=r"(dst[6]), "=r"(dst[7])
+              : "l"(src));
+        }
       }
     };
-    auto convert_item = [&](int k, const float (&src)[8], uint8_t* sA) {
+    auto convert_item = [&](int k, const uint32_t (&src)[IW], uint8_t* sA) {
       if (HP % WS_PXS == 0 || px0 + WS_PXS * k < HP) {
         uint4 hi;
         uint32_t* hp = reinterpret_cast<uint32_t*>(&hi);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) hp[e] = silu2_f16(fma2(pack2(src[2 * e], src[2 * e + 1]), sc2[e], sh2[e]));
+        for (int e = 0; e < 4; ++e) {
+          uint64_t x2;
+          if constexpr (IN16) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&src[e]));
+            x2 = pack2(f.x, f.y);
+          } else {
+            x2 = pack2(__uint_as_float(src[2 * e]), __uint_as_float(src[2 * e + 1]));
+          }
+          hp[e] = silu2_f16(fma2(x2, sc2[e], sh2[e]));
+        }
         *reinterpret_cast<uint4*>(sA + k * (WS_PXS * 16)) = hi;
       }
     };
@@ -657,7 +702,7 @@ conv128_ws_kernel(ConvParams p) {
           const int span = WX < p.W ? WX : p.W;
           int xs = tx2 * TW - KS / 2;
           xs = xs < 0 ? 0 : (xs > p.W - span ? p.W - span : xs);
-          bulk_prefetch_l2(p.in + ((int64_t(b2) * p.H + yy) * p.W + xs) * CC, uint32_t(span) * CC * 4);
+          bulk_prefetch_l2(in_b + ((int64_t(b2) * p.H + yy) * p.W + xs) * CC * ES, uint32_t(span) * CC * ES);
         }
       }
       if (it >= 2) mbar_wait(&bar_a_free[buf], ((it >> 1) - 1) & 1);
@@ -700,8 +745,8 @@ conv128_ws_kernel(ConvParams p) {
       const int y0 = ty * TH, x0 = tx * TW;
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      ws_drain_tile(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, y0, x0, tile, ew, lane, et, my_stage,
-                    warp_stage, s_bias, s_part[buf]);
+      ws_drain_tile<OUT16>(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, y0, x0, tile, ew, lane, et, my_stage,
+                           warp_stage, s_bias, s_part[buf]);
     }
   } else if (warp == WS_MMA_WARP) {
     // ============================================================================= MMA ISSUER
@@ -788,7 +833,7 @@ conv128_ws_kernel(ConvParams p) {
 #ifndef NAF_STEM_CTAS
 #define NAF_STEM_CTAS 2   // CTAs per SM of the tensor-core stem (43 KB smem, 256 TMEM columns each)
 #endif
-template <int KS>
+template <int KS, bool OUT16>
 __global__ void __launch_bounds__(WS_THREADS, NAF_STEM_CTAS)
 stem_tc_kernel(ConvParams p, const float* __restrict__ image, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
                const float* __restrict__ w) {
@@ -897,8 +942,8 @@ stem_tc_kernel(ConvParams p, const float* __restrict__ image, int64_t sb, int64_
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      ws_drain_tile(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, ty * TH, tx * TW, tile, ew, lane, et, my_stage,
-                    warp_stage, s_bias, s_part[buf]);
+      ws_drain_tile<OUT16>(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, ty * TH, tx * TW, tile, ew, lane, et,
+                           my_stage, warp_stage, s_bias, s_part[buf]);
     }
   } else if (warp == WS_MMA_WARP) {
     // ============================================================================= MMA ISSUER
@@ -934,11 +979,13 @@ stem_tc_kernel(ConvParams p, const float* __restrict__ image, int64_t sb, int64_
 // CTAs of 128 threads walk 16x8 tiles of one image; thread = 4 output channels (weights in registers,
 // loaded once per CTA) x 32 pixels per tile; the 3-channel halo tile sits in shared memory and is
 // read with warp-wide broadcasts.
-template <int KS>
+template <int KS, bool OUT16>
 __global__ void __launch_bounds__(128)
 stem_conv_kernel(const float* __restrict__ image, int64_t sb, int64_t sc, int64_t sy, int64_t sx,
-                 const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out,
+                 const float* __restrict__ w, const float* __restrict__ bias, void* __restrict__ out_v,
                  float* __restrict__ part, int H, int W, int tiles_x, int tiles) {
+  float* const out = static_cast<float*>(out_v);
+  __half* const out_h = static_cast<__half*>(out_v);
   constexpr int HY = TH + KS - 1, WX = TW + KS - 1, NK = 3 * KS * KS;
   __shared__ __align__(16) float s_in[HY * WX][4];   // [halo pixel][channel (3) + pad]
   __shared__ float s_red[4][8][2];
@@ -985,7 +1032,14 @@ stem_conv_kernel(const float* __restrict__ image, int64_t sb, int64_t sc, int64_
         }
       const int y = y0 + py, x = x0 + pxx;
       if (y < H && x < W) {
-        stg_stream(out + ((int64_t(b) * H + y) * W + x) * CC + 4 * q, acc);
+        if constexpr (OUT16) {
+          const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
+          asm volatile("st.global.cs.v2.b32 [%0], {%1, %2};" ::"l"(out_h + ((int64_t(b) * H + y) * W + x) * CC + 4 * q),
+                       "r"(*reinterpret_cast<const uint32_t*>(&h01)), "r"(*reinterpret_cast<const uint32_t*>(&h23))
+                       : "memory");
+        } else {
+          stg_stream(out + ((int64_t(b) * H + y) * W + x) * CC + 4 * q, acc);
+        }
         s += (acc.x + acc.y) + (acc.z + acc.w);
         ss += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
       }
@@ -1073,10 +1127,10 @@ __global__ void pack_conv_w_kernel(const float* __restrict__ w, __half* __restri
 // ------------------------------------------------------------------------------------ host side
 namespace {
 
-template <int KS>
+template <int KS, bool IN16, bool OUT16>
 int launch_conv_ws(const ConvParams& p, cudaStream_t st) {
   using Ws = WsConvCfg<KS>;
-  auto kern = conv128_ws_kernel<KS>;
+  auto kern = conv128_ws_kernel<KS, IN16, OUT16>;
   cudaError_t e = ensure_dyn_smem(kern, Ws::SMEM);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_conv: smem opt-in failed: %s", cudaGetErrorString(e));
   const int sms = device_sm_count();
@@ -1100,13 +1154,26 @@ int launch_conv(const ConvParams& p, cudaStream_t st) {
   return check_launch("enc_conv");
 }
 
+template <int KS>
+int launch_conv_ws_dt(const ConvParams& p, int in_dtype, int out_dtype, cudaStream_t st) {
+  const bool i16 = in_dtype == NAF_DTYPE_F16, o16 = out_dtype == NAF_DTYPE_F16;
+  if (i16 && o16) return launch_conv_ws<KS, true, true>(p, st);
+  if (i16) return launch_conv_ws<KS, true, false>(p, st);
+  if (o16) return launch_conv_ws<KS, false, true>(p, st);
+  return launch_conv_ws<KS, false, false>(p, st);
+}
+
 }  // namespace
 
-int launch_enc_conv(const float* in, const float* coef, const void* wpack, const float* bias, float* out,
+int launch_enc_conv(const void* in, const float* coef, const void* wpack, const float* bias, void* out,
                     int64_t out_pix_stride, int out_ch_off, float* part, int B, int H, int W, int KS,
-                    int passes, cudaStream_t st) {
+                    int passes, int in_dtype, int out_dtype, cudaStream_t st) {
   NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_conv: kernel size %d (1 or 3)", KS);
   NAF_REQUIRE(passes == 1 || passes == 3, NAF_ERR_UNSUPPORTED, "enc_conv: passes must be 1 or 3");
+  for (int dt : {in_dtype, out_dtype})
+    NAF_REQUIRE(dt == NAF_DTYPE_F32 || dt == NAF_DTYPE_F16, NAF_ERR_UNSUPPORTED, "enc_conv: activation dtype %d (0 = f32, 2 = f16)", dt);
+  NAF_REQUIRE(passes == 1 || (in_dtype == NAF_DTYPE_F32 && out_dtype == NAF_DTYPE_F32), NAF_ERR_UNSUPPORTED,
+              "enc_conv: fp16 activations belong to the 1-pass (TF32) class only");
   NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_conv: reflect padding needs H, W >= 2");
   NAF_REQUIRE(aligned32(in) && aligned16(wpack) && aligned16(out) && aligned16(coef) &&
                   out_pix_stride % 4 == 0 && out_ch_off % 4 == 0 && out_pix_stride >= out_ch_off + CC,
@@ -1128,13 +1195,15 @@ int launch_enc_conv(const float* in, const float* coef, const void* wpack, const
   p.tiles_y = (H + TH - 1) / TH;
   p.tiles_x = (W + TW - 1) / TW;
   // passes: 1 = 1-pass pipelined kernel (TF32 class), 3 = split-fp16 kernel (fp32 class)
-  if (KS == 1) return passes == 1 ? launch_conv_ws<1>(p, st) : launch_conv<1, 3>(p, st);
-  return passes == 1 ? launch_conv_ws<3>(p, st) : launch_conv<3, 3>(p, st);
+  if (KS == 1) return passes == 1 ? launch_conv_ws_dt<1>(p, in_dtype, out_dtype, st) : launch_conv<1, 3>(p, st);
+  return passes == 1 ? launch_conv_ws_dt<3>(p, in_dtype, out_dtype, st) : launch_conv<3, 3>(p, st);
 }
 
 int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
-                    const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st) {
+                    const float* bias, void* out, float* part, int B, int H, int W, int KS, int out_dtype,
+                    cudaStream_t st) {
   NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_stem: kernel size %d (1 or 3)", KS);
+  NAF_REQUIRE(out_dtype == NAF_DTYPE_F32 || out_dtype == NAF_DTYPE_F16, NAF_ERR_UNSUPPORTED, "enc_stem: out dtype %d", out_dtype);
   NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_stem: reflect padding needs H, W >= 2");
   NAF_REQUIRE(aligned16(out) && (!bias || aligned16(bias)), NAF_ERR_ALIGNMENT, "enc_stem: 16-byte alignment");
   NAF_REQUIRE(B <= 65535, NAF_ERR_UNSUPPORTED, "enc_stem: batch too large");
@@ -1143,16 +1212,21 @@ int launch_enc_stem(const float* image, int64_t sb, int64_t sc, int64_t sy, int6
   int per_img = (sms * 4 + B - 1) / B;   // ~4 CTAs of 128 threads per SM over the whole batch
   if (per_img > tiles) per_img = tiles;
   const dim3 grid(unsigned(per_img), unsigned(B), 1u);
-  prefer_max_shared(stem_conv_kernel<1>);
-  prefer_max_shared(stem_conv_kernel<3>);
-  if (KS == 1) stem_conv_kernel<1><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
-  else stem_conv_kernel<3><<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
+  auto go = [&](auto kern) {
+    prefer_max_shared(kern);
+    kern<<<grid, 128, 0, st>>>(image, sb, sc, sy, sx, w, bias, out, part, H, W, tiles_x, tiles);
+  };
+  const bool o16 = out_dtype == NAF_DTYPE_F16;
+  if (KS == 1) { if (o16) go(stem_conv_kernel<1, true>); else go(stem_conv_kernel<1, false>); }
+  else { if (o16) go(stem_conv_kernel<3, true>); else go(stem_conv_kernel<3, false>); }
   return check_launch("enc_stem");
 }
 
 int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, int64_t sx, const float* w,
-                       const float* bias, float* out, float* part, int B, int H, int W, int KS, cudaStream_t st) {
+                       const float* bias, void* out, float* part, int B, int H, int W, int KS, int out_dtype,
+                       cudaStream_t st) {
   NAF_REQUIRE(KS == 1 || KS == 3, NAF_ERR_UNSUPPORTED, "enc_stem_tc: kernel size %d (1 or 3)", KS);
+  NAF_REQUIRE(out_dtype == NAF_DTYPE_F32 || out_dtype == NAF_DTYPE_F16, NAF_ERR_UNSUPPORTED, "enc_stem_tc: out dtype %d", out_dtype);
   NAF_REQUIRE(KS == 1 || (H >= 2 && W >= 2), NAF_ERR_BAD_SHAPE, "enc_stem_tc: reflect padding needs H, W >= 2");
   NAF_REQUIRE(aligned16(out) && (!bias || aligned16(bias)), NAF_ERR_ALIGNMENT, "enc_stem_tc: 16-byte alignment");
   ConvParams p;
@@ -1176,16 +1250,15 @@ int launch_enc_stem_tc(const float* image, int64_t sb, int64_t sc, int64_t sy, i
   const int grid = int(total < cap ? total : cap);
   const int nch = KS == 3 ? 4 : 2;
   const int smem = 2 * nch * 128 * 16 + nch * CC * 16 + WS_NEPI * STAGE_SLOT;
-  cudaError_t e;
-  prefer_max_shared(stem_tc_kernel<1>);
-  prefer_max_shared(stem_tc_kernel<3>);
-  if (KS == 3) {
-    e = ensure_dyn_smem(stem_tc_kernel<3>, smem);
-    if (e == cudaSuccess) stem_tc_kernel<3><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
-  } else {
-    e = ensure_dyn_smem(stem_tc_kernel<1>, smem);
-    if (e == cudaSuccess) stem_tc_kernel<1><<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
-  }
+  cudaError_t e = cudaSuccess;
+  auto go = [&](auto kern) {
+    prefer_max_shared(kern);
+    e = ensure_dyn_smem(kern, smem);
+    if (e == cudaSuccess) kern<<<grid, WS_THREADS, smem, st>>>(p, image, sb, sc, sy, sx, w);
+  };
+  const bool o16 = out_dtype == NAF_DTYPE_F16;
+  if (KS == 3) { if (o16) go(stem_tc_kernel<3, true>); else go(stem_tc_kernel<3, false>); }
+  else { if (o16) go(stem_tc_kernel<1, true>); else go(stem_tc_kernel<1, false>); }
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "enc_stem_tc: smem opt-in failed: %s", cudaGetErrorString(e));
   return check_launch("enc_stem_tc");
 }

@@ -137,16 +137,25 @@ def _packed_weight(conv):
     return cache[1]
 
 
-def forward_tc(seq, image, out=None, ch_off=0, passes=None):
+def forward_tc(seq, image, out=None, ch_off=0, passes=None, act_dtype=None):
     """`seq(image)` on our kernels only: stem conv, then per EncBlock half one tiny coefficient
-    kernel and ONE fused GroupNorm+SiLU+conv kernel.  Returns the pixel-major (B,H,W,C_total)
+    kernel and ONE fused GroupNorm+SiLU+conv kernel.  Returns the pixel-major (B,H,W,C_total) fp32
     tensor `out` whose channels [ch_off, ch_off+128) hold the result (bias included); `out` is
-    allocated (128 channels) when not given."""
+    allocated (128 channels) when not given.
+
+    `act_dtype`: element type of the activations BETWEEN the layers.  Default: fp16 in the TF32 class
+    (passes = 1: the next layer rounds its input operand to fp16 anyway, so every layer moves half the
+    HBM bytes; GroupNorm statistics still come from the fp32 accumulators), fp32 in the strict class."""
     lib = _lib.load()
     dev = image.device
     x = image if image.dtype == torch.float32 else image.float()
     B, _, H, W = x.shape
     passes = conv_passes() if passes is None else int(passes)
+    if act_dtype is None:
+        act_dtype = torch.float16 if passes == 1 else torch.float32
+    if act_dtype not in (torch.float16, torch.float32) or (act_dtype == torch.float16 and passes != 1):
+        raise ValueError("forward_tc: fp16 activations belong to the 1-pass (TF32) class only")
+    act_code = _lib.DTYPE_F16 if act_dtype == torch.float16 else _lib.DTYPE_F32
     stem = seq[0]
     k = stem.kernel_size[0]
     tiles = -(-H // TILE_H) * -(-W // TILE_W)
@@ -155,21 +164,21 @@ def forward_tc(seq, image, out=None, ch_off=0, passes=None):
     if out is None:
         out = torch.empty((B, H, W, 128), device=dev, dtype=torch.float32)
         ch_off = 0
-    assert out.is_contiguous() and tuple(out.shape[:3]) == (B, H, W)
+    assert out.is_contiguous() and tuple(out.shape[:3]) == (B, H, W) and out.dtype == torch.float32
     pix_stride = out.shape[-1]
     part = torch.empty((B, tiles, 16), device=dev, dtype=torch.float32)
     coef = torch.empty((B, 128, 2), device=dev, dtype=torch.float32)
-    bufs = [torch.empty((B, H, W, 128), device=dev, dtype=torch.float32) for _ in range(min(2, len(layers)))]
+    bufs = [torch.empty((B, H, W, 128), device=dev, dtype=act_dtype) for _ in range(min(2, len(layers)))]
     sb, sc, sy, sx = x.stride()
     with torch.cuda.device(dev):
         last = len(layers) == 0
         y = out if last else bufs[0]
         # TF32 class, 3x3: the stem as a tensor-core GEMM (0.24 vs 0.40 ms at C2); the 1x1 stem (3 MACs per
         # output) and the strict class keep the exact-fp32 SIMT kernel (0.15 ms vs 0.21 ms on the GEMM path)
-        stem_fn = lib.naf_enc_stem_tc_f32 if (passes == 1 and k == 3) else lib.naf_enc_stem_f32
-        rc = stem_fn(ops._ptr(x), sb, sc, sy, sx, ops._ptr(stem.weight), ops._ptr(stem.bias),
-                     ops._ptr(y), ops._ptr(None if last else part), B, H, W, k, st)
-        _lib.check(rc, "naf_enc_stem_f32")
+        rc = lib.naf_enc_stem_ex(ops._ptr(x), sb, sc, sy, sx, ops._ptr(stem.weight), ops._ptr(stem.bias),
+                                 ops._ptr(y), ops._ptr(None if last else part), B, H, W, k,
+                                 1 if (passes == 1 and k == 3) else 0, _lib.DTYPE_F32 if last else act_code, st)
+        _lib.check(rc, "naf_enc_stem_ex")
         if last and (pix_stride != 128 or ch_off):
             raise NotImplementedError("stem-only encoder into a slab")
         for i, (norm, conv) in enumerate(layers):
@@ -178,11 +187,11 @@ def forward_tc(seq, image, out=None, ch_off=0, passes=None):
                                          ops._ptr(coef), B, H, W, float(norm.eps), st)
             _lib.check(rc, "naf_enc_gn_coef_f32")
             dst = out if last else bufs[(i + 1) & 1]
-            rc = lib.naf_enc_conv_f32(ops._ptr(y), ops._ptr(coef), ops._ptr(_packed_weight(conv)),
-                                      ops._ptr(conv.bias), ops._ptr(dst), pix_stride if last else 128,
-                                      ch_off if last else 0, ops._ptr(None if last else part), B, H, W, k,
-                                      passes, st)
-            _lib.check(rc, "naf_enc_conv_f32")
+            rc = lib.naf_enc_conv_ex(ops._ptr(y), ops._ptr(coef), ops._ptr(_packed_weight(conv)),
+                                     ops._ptr(conv.bias), ops._ptr(dst), pix_stride if last else 128,
+                                     ch_off if last else 0, ops._ptr(None if last else part), B, H, W, k,
+                                     passes, act_code, _lib.DTYPE_F32 if last else act_code, st)
+            _lib.check(rc, "naf_enc_conv_ex")
             y = dst
     return out
 

@@ -187,3 +187,88 @@ def test_bench_path_tf32_class_meets_the_bar_on_a_c2_shaped_case():
     err = (fast - strict).abs().max().item()
     print("C2-shaped: tf32-class vs strict-class whole-forward max|diff| =", err)
     assert err <= 9e-4
+
+
+# ------------------------------------------------------------------ fp16 activations between the layers (TF32 class)
+@pytest.mark.parametrize("io", [("f16", "f16"), ("f16", "f32"), ("f32", "f16")])
+@pytest.mark.parametrize("ks", [1, 3])
+@pytest.mark.parametrize("shape", [(1, 16, 8), (2, 40, 52), (1, 37, 29)])
+def test_gn_silu_conv_kernel_fp16_activations(ks, io, shape):
+    """naf_enc_conv_ex with fp16 input and / or output activations (1-pass class): same bar as the fp32-I/O 1-pass
+    kernel (4e-3 of the layer's max |value|); the partial sums are those of the fp32 accumulators."""
+    B, H, W = shape
+    torch.manual_seed(6)
+    norm = torch.nn.GroupNorm(8, 128)
+    conv = torch.nn.Conv2d(128, 128, ks, padding=ks // 2, padding_mode="reflect")
+    with torch.no_grad():
+        norm.weight.add_(0.3 * torch.randn(128))
+        norm.bias.add_(0.3 * torch.randn(128))
+    y = rnd(4, B, 128, H, W) * 1.7 + 0.4
+    in16, out16 = io[0] == "f16", io[1] == "f16"
+    y_nhwc = y.permute(0, 2, 3, 1).contiguous()
+    y_in = y_nhwc.half() if in16 else y_nhwc
+    y_seen = y_in.float().permute(0, 3, 1, 2)          # what the kernel reads, as NCHW
+    with torch.no_grad():
+        want = conv.double()(F.silu(norm.double()(y_seen.double()))).permute(0, 2, 3, 1).contiguous()
+    norm, conv = norm.float().to(dev()), conv.float().to(dev())
+    tiles = -(-H // 16) * -(-W // 8)
+    part = tile_partials(y_in.float()).float().view(B, tiles, 16).to(dev())
+    coef = torch.empty(B, 128, 2, device=dev())
+    lib, st = _lib.load(), ops._stream(dev())
+    _lib.check(lib.naf_enc_gn_coef_f32(ops._ptr(part), ops._ptr(norm.weight), ops._ptr(norm.bias), ops._ptr(coef),
+                                       B, H, W, float(norm.eps), st), "coef")
+    yd = y_in.to(dev())
+    out = torch.full((B, H, W, 128), 7.0, device=dev(), dtype=torch.float16 if out16 else torch.float32)
+    part_out = torch.full((B, tiles, 16), float("nan"), device=dev())
+    wpk = encoder_fast._packed_weight(conv)
+    code = {"f16": _lib.DTYPE_F16, "f32": _lib.DTYPE_F32}
+    _lib.check(lib.naf_enc_conv_ex(ops._ptr(yd), ops._ptr(coef), ops._ptr(wpk), ops._ptr(conv.bias), ops._ptr(out),
+                                   128, 0, ops._ptr(part_out), B, H, W, ks, 1, code[io[0]], code[io[1]], st), "conv")
+    got = out.cpu().double()
+    scale = want.abs().max().item()
+    err = (got - want).abs().max().item()
+    assert err <= 4e-3 * scale, (ks, io, shape, err, scale)
+    wp = tile_partials(want.float()).sum(dim=1)          # statistics of the (un-rounded) result
+    gp = part_out.cpu().double().view(B, tiles, 8, 2).sum(dim=1)
+    assert (gp - wp).abs().max().item() <= 4e-3 * max(1.0, wp.abs().max().item())
+    with pytest.raises(NotImplementedError):           # fp16 activations are a TF32-class feature
+        _lib.check(lib.naf_enc_conv_ex(ops._ptr(yd), ops._ptr(coef), ops._ptr(wpk), ops._ptr(conv.bias), ops._ptr(out),
+                                       128, 0, ops._ptr(part_out), B, H, W, ks, 3, _lib.DTYPE_F16, _lib.DTYPE_F16, st), "conv")
+
+
+@pytest.mark.parametrize("ks,tc", [(1, 0), (3, 0), (3, 1), (1, 1)])
+def test_stem_fp16_output(ks, tc):
+    B, H, W = 2, 40, 52
+    torch.manual_seed(2)
+    conv = torch.nn.Conv2d(3, 128, ks, padding=ks // 2, padding_mode="reflect")
+    x = rnd(3, B, 3, H, W)
+    with torch.no_grad():
+        want = conv.double()(x.double()).permute(0, 2, 3, 1).contiguous()
+    conv = conv.float().to(dev())
+    xd = x.to(dev())
+    tiles = -(-H // 16) * -(-W // 8)
+    out = torch.empty((B, H, W, 128), device=dev(), dtype=torch.float16)
+    part = torch.empty((B, tiles, 16), device=dev())
+    sb, sc, sy, sx = xd.stride()
+    rc = _lib.load().naf_enc_stem_ex(ops._ptr(xd), sb, sc, sy, sx, ops._ptr(conv.weight), ops._ptr(conv.bias),
+                                     ops._ptr(out), ops._ptr(part), B, H, W, ks, tc, _lib.DTYPE_F16, ops._stream(dev()))
+    _lib.check(rc, "stem")
+    scale = want.abs().max().item()
+    assert (out.cpu().double() - want).abs().max().item() <= (4e-3 if tc else 1e-3) * scale
+    wp = tile_partials(want.float())
+    assert (part.cpu().double().view(B, tiles, 8, 2) - wp).abs().max().item() <= 4e-3 * max(1.0, wp.abs().max().item())
+
+
+@pytest.mark.parametrize("ks", [1, 3])
+def test_whole_branch_fp32_activations_still_available(ks):
+    """The TF32-class branch with fp32 activations between the layers (round 1's data flow) stays selectable and
+    agrees with the default fp16-activation flow to the class tolerance."""
+    torch.manual_seed(3)
+    seq = encoder(3, 128, kernel_size=ks, ks_res=ks, num_layers=2).eval().to(dev())
+    img = rnd(9, 2, 3, 40, 52).to(dev())
+    a = encoder_fast.forward_tc(seq, img, passes=1, act_dtype=torch.float32)
+    b = encoder_fast.forward_tc(seq, img, passes=1)
+    scale = a.abs().max().item()
+    assert (a - b).abs().max().item() <= 8e-3 * scale
+    with pytest.raises(ValueError):
+        encoder_fast.forward_tc(seq, img, passes=3, act_dtype=torch.float16)
