@@ -163,7 +163,10 @@ enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2,
        NAF_ALGO_CELL_TC = 3 /* removed in ABI v3 (non-pipelined tensor-core kernel); requests fail with NAF_ERR_UNSUPPORTED */,
        NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline, windows converted in the kernel */,
        NAF_ALGO_CELL_TMA = 5  /* the same pipeline fed by tensor-map TMA: pre-split K / V planes, window boxes,
-                                  single-pass wide value heads, tensor stores (needs `workspace`) */ };
+                                  single-pass wide value heads, tensor stores (needs `workspace`) */,
+       NAF_ALGO_UNION_TC = 6  /* tensor-core path for tap tables (non-integer ratios), ratio 1 and tiny cells: dense
+                                  attention of an 8 x 16 pixel tile against the union of its windows under a
+                                  multiplicity mask, online softmax over 128-cell chunks (no score output) */ };
 
 NAF_API int naf_xattn_fwd_f32(const naf_xattn_params* p, void* stream);
 

@@ -15,10 +15,10 @@ LIB_PATH = os.environ.get("NAF_B200_LIB") or os.path.join(_HERE, "csrc", "libnaf
 ABI_VERSION = 3
 
 NAF_OK, NAF_ERR_BAD_SHAPE, NAF_ERR_UNSUPPORTED, NAF_ERR_WINDOW, NAF_ERR_ALIGNMENT, NAF_ERR_NULL, NAF_ERR_CUDA = range(7)
-ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS, ALGO_CELL_TMA = range(6)
+ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS, ALGO_CELL_TMA, ALGO_UNION_TC = range(7)
 # (3 was the non-pipelined tensor-core kernel, removed in ABI v3; the value stays reserved)
 ALGO_NAMES = {ALGO_AUTO: "auto", ALGO_GENERIC: "generic", ALGO_CELL_SIMT: "cell_simt", ALGO_CELL_TCWS: "cell_tcws",
-              ALGO_CELL_TMA: "cell_tma"}
+              ALGO_CELL_TMA: "cell_tma", ALGO_UNION_TC: "union_tc"}
 
 _fp = C.c_void_p  # device pointers travel as integers
 

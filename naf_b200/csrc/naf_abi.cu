@@ -152,6 +152,10 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
     if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
     return -fail(NAF_ERR_UNSUPPORTED, "xattn: SIMT cell kernel unsupported: %s", why);
   }
+  if (p.algo == NAF_ALGO_UNION_TC) {
+    if (xattn_union_tc_supported(p, &why)) return NAF_ALGO_UNION_TC;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: union-window tensor-core kernel unsupported: %s", why);
+  }
   if (p.algo != NAF_ALGO_AUTO) return -fail(NAF_ERR_UNSUPPORTED, "xattn: unknown algo %d", p.algo);
   (void)explain;
   const bool tma_ok = xattn_cell_tma_supported(p, &why);
@@ -169,7 +173,14 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
   }
   if (tma_ok) return NAF_ALGO_CELL_TMA;
   if (ws_ok) return NAF_ALGO_CELL_TCWS;
-  if (xattn_cell_simt_supported(p, &why)) return NAF_ALGO_CELL_SIMT;
+  // Everything the pipelined cell kernels refuse: tap tables (non-integer ratios), ratio 1, cells of a few pixels,
+  // head dims other than 64, K > 11.  Measured (scripts/check_union.py, profiles/r2_union_tc.txt): the union-window
+  // tensor-core kernel is 7-36x faster than the warp-per-pixel kernel and 2.5x faster than the fp32 cell kernel
+  // at K = 13; the fp32 cell kernel keeps narrow heads (dq <= 32: 0.81 vs 0.92 ms at r = 14).
+  const bool simt_ok = xattn_cell_simt_supported(p, &why);
+  const bool union_ok = xattn_union_tc_supported(p, &why);
+  if (simt_ok && (!union_ok || p.D / p.heads <= 32)) return NAF_ALGO_CELL_SIMT;
+  if (union_ok) return NAF_ALGO_UNION_TC;
   return NAF_ALGO_GENERIC;
 }
 
@@ -305,6 +316,8 @@ int naf_xattn_fwd_f32(const naf_xattn_params* pp, void* stream) {
       return launch_xattn_cell_tcws(p, st);
     case NAF_ALGO_CELL_SIMT:
       return launch_xattn_cell_simt(p, st);
+    case NAF_ALGO_UNION_TC:
+      return launch_xattn_union_tc(p, st);
     default:
       return launch_xattn_generic(p, st);
   }

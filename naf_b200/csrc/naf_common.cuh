@@ -145,6 +145,8 @@ int launch_xattn_cell_tcws(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_tma_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_tma(const naf_xattn_params& p, cudaStream_t st);
 size_t xattn_cell_tma_workspace(const naf_xattn_params& p);
+bool xattn_union_tc_supported(const naf_xattn_params& p, const char** why);
+int launch_xattn_union_tc(const naf_xattn_params& p, cudaStream_t st);
 int launch_concat_bias(const float* a, const float* bias_a, int Ca, const float* b, const float* bias_b,
                        int Cb, float* out, int64_t npix, cudaStream_t st);
 int launch_gn_stats(const float* y, const float* bias, double* sums, int B, int64_t HW, int C, int G,

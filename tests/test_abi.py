@@ -63,7 +63,11 @@ def test_kernel_selection_for_baseline_configs():
     assert sel((4, 256, 1036, 1036), (4, 1024, 37, 37), 4, 11) == "cell_tma"   # C3: single-pass wide heads
     assert sel((16, 256, 1344, 1344), (16, 768, 24, 24), 4, 7) == "cell_tcws"  # C4: 56x56-pixel cells
     assert sel((4, 256, 2048, 2048), (4, 768, 32, 32), 4, 7) == "cell_tcws"    # C5: 64x64-pixel cells
-    assert sel((1, 64, 32, 32), (1, 16, 13, 13), 4, 9) == "generic"     # non-integer ratio
+    assert sel((1, 64, 32, 32), (1, 16, 13, 13), 4, 9) == "union_tc"    # non-integer ratio (tap tables)
+    assert sel((8, 256, 32, 32), (8, 384, 13, 13), 4, 9) == "union_tc"  # the reference's training shape
+    assert sel((8, 256, 256, 256), (8, 3, 256, 256), 1, 15) == "union_tc"  # denoising: ratio 1, C = 3, one head
+    assert sel((1, 64, 32, 32), (1, 16, 13, 13), 4, 9, return_scores=True) == "generic"   # per-tap scores
+    assert sel((1, 96, 32, 32), (1, 16, 13, 13), 4, 9) == "generic"     # head dim 24: not a multiple of 16
     assert sel((1, 256, 36, 36), (1, 32, 9, 9), 4, 7, return_scores=True) == "generic"      # 16-pixel cells
     assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7, return_scores=True) == "cell_tma"  # scores on the fast kernel
 

@@ -26,27 +26,31 @@ def dev():
 
 
 def tol_for(algo):
-    return TOL_BAR if algo in (_lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA) else TOL_FP32
+    return TOL_BAR if algo in (_lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA, _lib.ALGO_UNION_TC) else TOL_FP32
 
 
 def available_algos(q_shape, v_shape, heads, K):
     """Every kernel able to run this problem (each is tested, not just AUTO's pick)."""
+    import ctypes as C
     algos = [_lib.ALGO_GENERIC]
     Ho, Wo, h, w = q_shape[2], q_shape[3], v_shape[2], v_shape[3]
-    if Ho % h == 0 and Wo % w == 0:
-        for algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA):
-            p = _lib.XAttnParams()
-            d = 1 << 20
-            p.q = p.k = p.v = p.out = d
-            p.workspace, p.workspace_bytes = d, 1 << 62
-            p.B, p.D, p.C, p.heads = q_shape[0], q_shape[1], v_shape[1], heads
-            p.Ho, p.Wo, p.h, p.w, p.K = Ho, Wo, h, w, K
-            p.scale = 1.0
-            p.q_stride_b, p.q_stride_y, p.q_stride_x = Ho * Wo * q_shape[1], Wo * q_shape[1], q_shape[1]
-            p.algo = algo
-            import ctypes as C
-            if _lib.load().naf_xattn_select_algo(C.byref(p)) == algo:
-                algos.append(algo)
+    integer = Ho % h == 0 and Wo % w == 0
+    for algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA, _lib.ALGO_UNION_TC):
+        if not integer and algo != _lib.ALGO_UNION_TC:
+            continue
+        p = _lib.XAttnParams()
+        d = 1 << 20
+        p.q = p.k = p.v = p.out = d
+        if not integer:
+            p.row_tap = p.col_tap = d
+        p.workspace, p.workspace_bytes = d, 1 << 62
+        p.B, p.D, p.C, p.heads = q_shape[0], q_shape[1], v_shape[1], heads
+        p.Ho, p.Wo, p.h, p.w, p.K = Ho, Wo, h, w, K
+        p.scale = 1.0
+        p.q_stride_b, p.q_stride_y, p.q_stride_x = Ho * Wo * q_shape[1], Wo * q_shape[1], q_shape[1]
+        p.algo = algo
+        if _lib.load().naf_xattn_select_algo(C.byref(p)) == algo:
+            algos.append(algo)
     return algos
 
 
@@ -142,6 +146,16 @@ ORACLE_CASES = [
     (1, 64, 4, 200, 48, 48, 8, 8, 3, 1.0),        # dq=16, dv=50 (generic only)
     (1, 256, 4, 60, 45, 45, 9, 9, 5, 1.0),        # r=5: cells of 25 pixels (small-cell path)
     (1, 256, 2, 6, 40, 40, 8, 8, 7, 8.0),         # dq=128 (generic), very peaky
+    # tap-table / ratio-1 / tiny-cell shapes: the union-window tensor-core kernel (and the generic one)
+    (2, 256, 4, 384, 32, 32, 13, 13, 9, 2.0),     # the reference's training shape 32 <- 13 (duplicated taps)
+    (1, 256, 4, 768, 32, 32, 19, 19, 9, 1.0),     # 32 <- 19: ratio 1.68, dilation 1
+    (1, 256, 4, 1024, 37, 41, 16, 18, 9, 3.0),    # dv = 256, non-square, partial tiles
+    (2, 96, 1, 3, 40, 52, 40, 52, 15, 4.0),       # denoising: ratio 1, C = 3, one head, K = 15 (6 chunks)
+    (1, 256, 1, 3, 48, 48, 48, 48, 11, 2.0),      # denoising dim 256: dq = 256
+    (1, 128, 1, 4, 33, 35, 33, 35, 7, 1.0),       # heads 1-4 variant, odd sizes
+    (1, 256, 4, 384, 56, 56, 28, 28, 9, 2.0),     # integer ratio 2: 4-pixel cells
+    (1, 64, 2, 10, 30, 45, 7, 11, 3, 4.0),        # ratio 4.3 / 4.1, dv = 5
+    (1, 256, 4, 200, 45, 33, 9, 11, 5, 1.0),      # dv = 50: padded value head, scalar loads
 ]
 
 
@@ -467,3 +481,33 @@ def test_bf16_inputs_are_read_natively(case, layout):
     # the other kernels take fp32 only: a forced kernel still works (the Python layer widens for it)
     gen = ops.xattn(q, k, v, n, K, algo=_lib.ALGO_GENERIC)
     assert (gen - want).abs().max().item() <= TOL_BAR
+
+
+# ------------------------------------------------------------------ union-window tensor-core kernel
+def test_union_kernel_is_the_auto_path_for_tap_tables():
+    """Non-integer ratios (the reference's training shape 32 <- 13, utils/training.py:28-50) and ratio 1
+    (denoising.py:209-213) run on the tensor-core union kernel under AUTO -- not on the warp-per-pixel kernel --
+    with bf16 stores and on-the-fly RoPE, and agree with the fp32 generic kernel to the 1e-3 bar (measured 1e-5)."""
+    for (B, D, n, Cv, Ho, Wo, h, w, K) in [(2, 256, 4, 384, 32, 32, 13, 13, 9), (1, 96, 1, 3, 40, 36, 40, 36, 15)]:
+        q, k, v = rnd(1, B, D, Ho, Wo).to(dev()) * 2.0, rnd(2, B, D, h, w).to(dev()), rnd(3, B, Cv, h, w).to(dev())
+        tabs = naf_b200.RoPE(D, num_heads=n, base=100.0, rescale_coords=2.0).eval().to(dev()).axis_tables(Ho, Wo)
+        assert ops.select_algo(q.shape, v.shape, n, K) == "union_tc"
+        n0, g0 = ops.launch_count("xattn_union_tc"), ops.launch_count("xattn_generic")
+        got = ops.xattn(q, k, v, n, K, rope_tables=tabs)
+        got16 = ops.xattn(q, k, v, n, K, rope_tables=tabs, out_dtype=torch.bfloat16)
+        assert ops.launch_count("xattn_union_tc") == n0 + 2 and ops.launch_count("xattn_generic") == g0
+        want = ops.xattn(q, k, v, n, K, rope_tables=tabs, algo=_lib.ALGO_GENERIC)
+        assert (got - want).abs().max().item() <= 1e-4
+        assert got16.dtype == torch.bfloat16 and torch.equal(got16, got.to(torch.bfloat16))
+
+
+def test_union_kernel_reads_replicated_guidance():
+    """`rep` (guidance stored at the encoder resolution) through the union kernel: 2-pixel cells."""
+    B, D, Cv, Hs, Ws, K, rep = 1, 256, 64, 20, 24, 5, (2, 2)
+    Ho, Wo, h, w = Hs * 2, Ws * 2, 20, 24
+    xs, feats = rnd(7, B, D, Hs, Ws), rnd(8, B, Cv, h, w)
+    want = O.naf_forward(xs.repeat_interleave(2, 2).repeat_interleave(2, 3), feats, 4, 4, K)
+    model = naf_b200.NAF(kernel_size=K).eval().to(dev())
+    model.upsampler.algo = _lib.ALGO_UNION_TC
+    got = model.upsample_from_guidance(xs.to(dev()), feats.to(dev()), rep=rep)
+    assert (got.cpu() - want).abs().max().item() <= 5e-5
