@@ -160,7 +160,8 @@ typedef struct naf_xattn_params {
 enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1, NAF_DTYPE_F16 = 2 /* encoder activations only */ };
 
 enum { NAF_ALGO_AUTO = 0, NAF_ALGO_GENERIC = 1, NAF_ALGO_CELL_SIMT = 2,
-       NAF_ALGO_CELL_TC = 3 /* removed in ABI v3 (non-pipelined tensor-core kernel); requests fail with NAF_ERR_UNSUPPORTED */,
+       NAF_ALGO_CELL_TC = 3 /* non-pipelined tensor-core cell kernel: the forward one was removed in ABI v3 (forward
+                               requests fail with NAF_ERR_UNSUPPORTED); naf_xattn_bwd_f32 has one (naf_xattn_bwd_tc.cu) */,
        NAF_ALGO_CELL_TCWS = 4 /* warp-specialised persistent tcgen05 pipeline, windows converted in the kernel */,
        NAF_ALGO_CELL_TMA = 5  /* the same pipeline fed by tensor-map TMA: pre-split K / V planes, window boxes,
                                   single-pass wide value heads, tensor stores (needs `workspace`) */,
@@ -182,7 +183,9 @@ NAF_API size_t naf_xattn_workspace_bytes(const naf_xattn_params* p);
  * backward: the probabilities are recomputed); dout is dL/dout, (B,Ho,Wo,C) contiguous fp32.  Outputs:
  *   dq (B,Ho,Wo,D) contiguous : gradient w.r.t. the ROTATED queries (= w.r.t. q when no rope tables);
  *   dk (B,h,w,D), dv (B,h,w,C): zeroed by the call, then accumulated (scatter-add over the windows).
- * algo: NAF_ALGO_AUTO (cell kernel for integer ratios, else generic), NAF_ALGO_GENERIC, NAF_ALGO_CELL_SIMT.
+ * algo: NAF_ALGO_AUTO (tensor-core cell kernel for integer ratios with 64-wide heads and cells of >= 64 pixels,
+ * else the fp32 cell kernel, else generic), NAF_ALGO_GENERIC, NAF_ALGO_CELL_SIMT, NAF_ALGO_CELL_TC (the tensor-core
+ * cell kernel: five tcgen05 GEMMs per 128-pixel tile, window gradients accumulated in TMEM over the whole cell).
  * ---------------------------------------------------------------------------------------- */
 typedef struct naf_xattn_bwd_params {
   const float* q;

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 LIB = os.path.join(HERE, "libnaf_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 SOURCES = ["naf_abi.cu", "naf_pack.cu", "naf_kpool.cu", "naf_xattn_generic.cu", "naf_xattn_simt.cu",
-           "naf_xattn_tcws.cu", "naf_xattn_tma.cu", "naf_xattn_union.cu", "naf_xattn_bwd.cu", "naf_encoder.cu", "naf_conv_tc.cu"]
+           "naf_xattn_tcws.cu", "naf_xattn_tma.cu", "naf_xattn_union.cu", "naf_xattn_bwd.cu", "naf_xattn_bwd_tc.cu", "naf_encoder.cu", "naf_conv_tc.cu"]
 HEADERS = ["naf_common.cuh", "naf_umma.cuh", "naf_tmap.cuh", os.path.join(ROOT, "include", "naf_b200.h")]
 
 

@@ -262,8 +262,8 @@ int naf_xattn_bwd_f32(const naf_xattn_bwd_params* pp, void* stream) {
   f.rep_y = p.rep_y; f.rep_x = p.rep_x;
   int rc = validate_xattn(f);
   if (rc != NAF_OK) return rc;
-  NAF_REQUIRE(p.algo == NAF_ALGO_AUTO || p.algo == NAF_ALGO_GENERIC || p.algo == NAF_ALGO_CELL_SIMT, NAF_ERR_UNSUPPORTED,
-              "xattn_bwd: algo %d (auto, generic or cell_simt)", p.algo);
+  NAF_REQUIRE(p.algo == NAF_ALGO_AUTO || p.algo == NAF_ALGO_GENERIC || p.algo == NAF_ALGO_CELL_SIMT || p.algo == NAF_ALGO_CELL_TC,
+              NAF_ERR_UNSUPPORTED, "xattn_bwd: algo %d (auto, generic, cell_simt or cell_tc)", p.algo);
   return launch_xattn_bwd(p, static_cast<cudaStream_t>(stream));
 }
 

@@ -138,6 +138,8 @@ int launch_rope_kpool(const naf_kpool_params& p, cudaStream_t st);
 int launch_xattn_generic(const naf_xattn_params& p, cudaStream_t st);
 int launch_xattn_bwd(const naf_xattn_bwd_params& p, cudaStream_t st);
 int launch_rope_kpool_bwd(const naf_kpool_bwd_params& p, cudaStream_t st);
+bool xattn_bwd_cell_tc_supported(const naf_xattn_bwd_params& p, const char** why);
+int launch_xattn_bwd_cell_tc(const naf_xattn_bwd_params& p, cudaStream_t st);
 bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why);
 int launch_xattn_cell_simt(const naf_xattn_params& p, cudaStream_t st);
 bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why);

@@ -452,6 +452,14 @@ int launch_xattn_bwd(const naf_xattn_bwd_params& p, cudaStream_t st) {
   if (e == cudaSuccess) e = cudaMemsetAsync(p.dv, 0, sizeof(float) * size_t(p.B) * p.h * p.w * p.C, st);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn_bwd: memset failed: %s", cudaGetErrorString(e));
   const int dq = p.D / p.heads, dv = p.C / p.heads, K2 = p.K * p.K;
+  {
+    // integer ratios, 64-wide heads, cells of >= 64 pixels: the five GEMMs on the tensor core (naf_xattn_bwd_tc.cu)
+    const char* why = "";
+    const bool tc_ok = xattn_bwd_cell_tc_supported(p, &why);
+    if (tc_ok && (p.algo == NAF_ALGO_AUTO || p.algo == NAF_ALGO_CELL_TC)) return launch_xattn_bwd_cell_tc(p, st);
+    if (p.algo == NAF_ALGO_CELL_TC)
+      return fail(NAF_ERR_UNSUPPORTED, "xattn_bwd: the tensor-core cell kernel does not support this request: %s", why);
+  }
   const int cell_nt = p.algo != NAF_ALGO_GENERIC ? bwd_cell_config(p) : 0;
   if (cell_nt) return dq == 64 ? launch_bwd_cell<64>(p, cell_nt, st) : launch_bwd_cell<32>(p, cell_nt, st);
   if (p.algo == NAF_ALGO_CELL_SIMT)

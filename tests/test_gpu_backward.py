@@ -3,8 +3,8 @@ against (1) gradient fixtures produced by autograd through the UNMODIFIED refere
 (tests/golden/bwd_*.npz), (2) the fp64 oracle on seeded inputs (gradcheck-style: the same loss, the
 same upstream gradient), for every backward kernel able to run the case.
 
-Tolerance: the kernels are plain fp32 with atomics (summation order varies): 3e-5 of the gradient's
-max |value| against fp64 / the reference's fp32."""
+Tolerance: fp32 SIMT kernels with atomics (summation order varies) and the tensor-core cell kernel (three-pass
+split-fp16 GEMMs, fp32 accumulation): 3e-5 of the gradient's max |value| against fp64 / the reference's fp32."""
 import numpy as np
 import pytest
 import torch
@@ -33,11 +33,16 @@ def close(got, want, what, rel=REL):
     assert err <= rel * scale + 1e-7, (what, err, scale)
 
 
-def bwd_algos(q_shape, v_shape):
-    Ho, Wo, h, w = q_shape[2], q_shape[3], v_shape[2], v_shape[3]
-    algos = [_lib.ALGO_GENERIC]
-    if Ho % h == 0 and Wo % w == 0:
-        algos.append(_lib.ALGO_AUTO)     # the cell kernel when it supports the shape
+def bwd_algos(q, k, v, dout, heads, K):
+    """Every backward kernel able to run the case: generic always; the fp32 cell kernel and the tensor-core cell
+    kernel where they accept it (asked for explicitly, so AUTO's choice cannot hide one of them)."""
+    algos = [_lib.ALGO_GENERIC, _lib.ALGO_AUTO]
+    for algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TC):
+        try:
+            ops.xattn_bwd(q, k, v, dout, heads, K, algo=algo)
+            algos.append(algo)
+        except NotImplementedError:
+            pass
     return algos
 
 
@@ -45,7 +50,7 @@ def bwd_algos(q_shape, v_shape):
 def test_operator_gradients_match_reference_golden(name):
     c = G.bwd_attention_case(name)
     q, k, v, dout = (c[n].to(dev()) for n in ("q", "k", "v", "dout"))
-    for algo in bwd_algos(q.shape, v.shape):
+    for algo in bwd_algos(q, k, v, dout, c["heads"], c["K"]):
         dq, dk, dv = ops.xattn_bwd(q, k, v, dout, c["heads"], c["K"], algo=algo)
         close(dq, c["dq"], (name, algo, "dq"))
         close(dk, c["dk"], (name, algo, "dk"))
@@ -110,6 +115,9 @@ GRAD_CASES = [
     (1, 256, 4, 1, 32, 30, 30, (1, 1), 10, 10, 3),     # rope heads != attention heads: composed operators
     (1, 256, 4, 4, 1024, 44, 44, (1, 1), 11, 11, 11),  # K=11, dv=256: the 512-thread cell configuration
     (1, 96, 1, 1, 3, 20, 22, (1, 1), 20, 22, 15),      # denoising shape: r=1, one head of 96, C=3
+    (1, 256, 4, 4, 768, 98, 98, (1, 1), 7, 7, 7),      # C2-like cells (r=14, dv=192): tensor-core kernel, 3 value chunks
+    (1, 256, 4, 4, 768, 88, 88, (1, 1), 11, 11, 11),   # K=11, dv=192: tensor-core kernel with all 512 TMEM columns
+    (2, 256, 4, 4, 384, 72, 90, (1, 1), 9, 9, 9),      # the backward benchmark's K=9, dv=96 (chunks of 64 + 32), r=8x10
 ]
 
 
@@ -147,6 +155,27 @@ def test_kernel_choice_and_determinism_of_dq():
     for i in range(3):
         close(a[i], g[i].cpu(), ("cell vs generic", i))
         close(a[i], b[i].cpu(), ("run to run", i), rel=1e-5)
+
+
+def test_tensor_core_backward_is_the_auto_path():
+    """Integer ratios with 64-wide heads and cells of >= 64 pixels (every row of test/backward_speed.py from ratio 8
+    up) run on the tensor-core cell kernel; dq is bit-reproducible, the three kernels agree."""
+    q, k, v, dout = rnd(1, 2, 256, 112, 112).to(dev()) * 2, rnd(2, 2, 256, 14, 14).to(dev()), rnd(3, 2, 384, 14, 14).to(dev()), \
+        rnd(4, 2, 384, 112, 112).to(dev())
+    n0 = ops.launch_count("xattn_bwd_cell_tc")
+    a = ops.xattn_bwd(q, k, v, dout, 4, 9)
+    b = ops.xattn_bwd(q, k, v, dout, 4, 9)
+    assert ops.launch_count("xattn_bwd_cell_tc") == n0 + 2
+    assert torch.equal(a[0], b[0])
+    s = ops.xattn_bwd(q, k, v, dout, 4, 9, algo=_lib.ALGO_CELL_SIMT)
+    g = ops.xattn_bwd(q, k, v, dout, 4, 9, algo=_lib.ALGO_GENERIC)
+    for i in range(3):
+        close(a[i], s[i].cpu(), ("tc vs simt", i))
+        close(a[i], g[i].cpu(), ("tc vs generic", i))
+        close(a[i], b[i].cpu(), ("run to run", i), rel=1e-5)
+    with pytest.raises(NotImplementedError):        # 49-pixel cells: not the tensor-core kernel's shape
+        ops.xattn_bwd(rnd(1, 1, 256, 56, 56).to(dev()), rnd(2, 1, 256, 8, 8).to(dev()), rnd(3, 1, 96, 8, 8).to(dev()),
+                      rnd(4, 1, 96, 56, 56).to(dev()), 4, 5, algo=_lib.ALGO_CELL_TC)
 
 
 def test_training_step_moves_the_loss():
