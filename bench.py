@@ -23,6 +23,8 @@ Rank 0 prints ONE JSON line.  Keys beyond the base contract:
                (where both byte counts coincide)
   configs      whole-forward ms, attention ms and roofline fraction for the other BASELINE.json configs
                (C1, C3 [4 images per GPU: B=32 over 8 GPUs], C4, C5)
+  other_paths  operator-level kernel timings of the paths the headline step does not exercise: the backward
+               (tensor-core cell kernel) and the tap-table / ratio-1 forward (union-window tensor-core kernel)
   cpu_baseline the UNMODIFIED reference modules (oracle/_ref, NATTEN replaced by oracle/natten_stub.py) on
                the host cores, bounded sample (N=1, rank 0 only)
 """
@@ -272,6 +274,68 @@ def xattn_bytes(B, C, to, lo, src):
     return real, algo
 
 
+def other_paths(dev, peak):
+    """Operator-level timings (kernels only, tensors resident, CUDA events, N = 1) of the paths the headline step
+    does not exercise: the backward and the tap-table / ratio-1 forward (8f-3).  `frac` rates
+    each launch on its algorithmic bytes: forward 4*(D + C) per pixel, backward 4*(C + 2*D) per pixel (dout and
+    q read once, dq written once; windows and their gradients are < 1 %)."""
+    import naf_b200
+    from naf_b200 import _lib, ops
+
+    def time_op(fn, n=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    def entry(ms, nbytes, kernel):
+        gbs = nbytes / (ms / 1e3) / 1e9
+        return {"ms": round(ms, 4), "kernel": kernel, "bytes": int(nbytes), "achieved": round(gbs, 1), "unit": "GB/s",
+                "frac": round(gbs / peak, 4)}
+
+    out = {}
+    g = torch.Generator(device="cpu").manual_seed(7)
+    D = D_GUIDE
+    # ---- backward at the reference's own backward benchmark (test/backward_speed.py: B=1, 448 <- 28, K=9) and on
+    # one C2 image (896 <- 32, K=7, C=768)
+    for name, (B, C, to, lo, K) in {"bwd_ref_protocol_c384": (1, 384, 448, 28, 9), "bwd_c2_image": (1, 768, 896, 32, 7)}.items():
+        q = torch.randn(B, D, to, to, generator=g).to(dev)
+        k = torch.randn(B, D, lo, lo, generator=g).to(dev)
+        v = torch.randn(B, C, lo, lo, generator=g).to(dev)
+        dout = torch.randn(B, C, to, to, generator=g).to(dev)
+        tabs = naf_b200.RoPE(D, num_heads=4, base=100.0, rescale_coords=2.0).eval().to(dev).axis_tables(to, to)
+        n0 = ops.launch_count("xattn_bwd_cell_tc")
+        ms_b = time_op(lambda: ops.xattn_bwd(q, k, v, dout, 4, K, rope_tables=tabs))
+        kern = "xattn_bwd (cell_tc)" if ops.launch_count("xattn_bwd_cell_tc") > n0 else "xattn_bwd (simt)"
+        ms_f = time_op(lambda: ops.xattn(q, k, v, 4, K, rope_tables=tabs))
+        out[name] = {"shape": f"B={B} C={C} {to}x{to} <- {lo}x{lo} K={K}",
+                     "backward": entry(ms_b, 4.0 * B * to * to * (C + 2 * D), kern),
+                     "forward": entry(ms_f, 4.0 * B * to * to * (C + D), "xattn (" + ops.select_algo(q.shape, v.shape, 4, K) + ")"),
+                     "host_overhead_note": "both through naf_b200.ops (Python + ctypes): ~0.08 ms of host time per call bounds the small shapes"}
+        del q, k, v, dout
+    # ---- tap-table / ratio-1 forward: the reference's training shape (utils/training.py:28-50) and its denoising
+    # shape (denoising.py:209-213,436-451) on the union-window tensor-core kernel vs the warp-per-pixel kernel
+    for name, (B, Dq, n, C, to, lo, K) in {"train_32_from_13": (8, 256, 4, 384, 32, 13, 9),
+                                           "denoise_256_r1_k15": (2, 256, 1, 3, 256, 256, 15)}.items():
+        q = torch.randn(B, Dq, to, to, generator=g).to(dev)
+        k = torch.randn(B, Dq, lo, lo, generator=g).to(dev)
+        v = torch.randn(B, C, lo, lo, generator=g).to(dev)
+        tabs = naf_b200.RoPE(Dq, num_heads=n, base=100.0, rescale_coords=2.0).eval().to(dev).axis_tables(to, to)
+        ms_u = time_op(lambda: ops.xattn(q, k, v, n, K, rope_tables=tabs))
+        ms_g = time_op(lambda: ops.xattn(q, k, v, n, K, rope_tables=tabs, algo=_lib.ALGO_GENERIC), n=3)
+        out[name] = {"shape": f"B={B} D={Dq} heads={n} C={C} {to}x{to} <- {lo}x{lo} K={K}",
+                     "auto": entry(ms_u, 4.0 * B * to * to * (C + Dq), "xattn (" + ops.select_algo(q.shape, v.shape, n, K) + ")"),
+                     "generic_ms": round(ms_g, 4)}
+        del q, k, v
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -279,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
-    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tcws", "cell_tma"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "generic", "cell_simt", "cell_tcws", "cell_tma", "union_tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-d2h", default="full", choices=["full", "sample", "both"],
                     help="what the e2e step reads back: the whole result (default; `e2e`), one value per "
@@ -287,6 +351,8 @@ def main():
     ap.add_argument("--configs", default="C1,C3,C4,C5",
                     help="other BASELINE.json configs reported in the `configs` block ('' = none)")
     ap.add_argument("--config-steps", type=int, default=5)
+    ap.add_argument("--no-other-paths", action="store_true",
+                    help="skip the `other_paths` block (backward and tap-table kernels at operator level)")
     ap.add_argument("--graph", type=int, default=0,
                     help="1: also time NAF.forward replayed as a CUDA graph (naf_b200.GraphedNAF)")
     args = ap.parse_args()
@@ -541,6 +607,14 @@ def main():
         if "C3" in line["configs"] and "error" not in line["configs"]["C3"]:
             line["configs"]["C3"]["note"] = (f"BASELINE.json configs[2] = batch 32 sharded over 8 GPUs = 4 images per GPU; "
                                              f"this run: {world} GPU(s), global batch {4 * world}")
+
+    # ============================================================ the other kernels behind the same operator API
+    if world == 1 and not args.no_other_paths:
+        try:
+            line["other_paths"] = other_paths(dev, peak)
+        except Exception as exc:
+            line["other_paths"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+        torch.cuda.empty_cache()
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

@@ -24,6 +24,10 @@
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
+#ifndef NAF_BWD_EXP
+#define NAF_BWD_EXP 0   // profiling experiments only (scripts/gpu_bwd_exp.sh); 0 in every real build
+#endif
+
 namespace naf {
 
 using namespace umma;
@@ -59,7 +63,7 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 
 template <int TP>
 __global__ void __launch_bounds__(NT, 1)
-xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
+xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_resident) {
   using Cfg = BwdCfg<TP>;
   constexpr int SC = TP / 2;   // S / dP columns per thread
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -70,9 +74,12 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
 
   uint8_t* sKhi = smem;
   uint8_t* sKlo = sKhi + Cfg::kWin;
+  // V window: [channel group][tap][16 B]; the whole value head when it fits (staged once per cell), else one
+  // 64-channel chunk restaged per tile and chunk
+  const int v_img = (v_resident ? (dv >> 3) : KC) * TP * 16;
   uint8_t* sVhi = sKlo + Cfg::kWin;
-  uint8_t* sVlo = sVhi + Cfg::kWin;
-  uint8_t* sQhi = sVlo + Cfg::kWin;
+  uint8_t* sVlo = sVhi + v_img;
+  uint8_t* sQhi = sVlo + v_img;
   uint8_t* sQlo = sQhi + PIXIMG;
   uint8_t* sGhi = sQlo + PIXIMG;
   uint8_t* sGlo = sGhi + PIXIMG;
@@ -174,7 +181,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int g8 = hf + 2 * k;
-      if (px.valid && g8 < ng) {
+      if (px.valid && g8 < ng && !(NAF_BWD_EXP & 16)) {
         g4[k][0] = ldg_stream(gp + g8 * 8);
         g4[k][1] = ldg_stream(gp + g8 * 8 + 4);
       } else {
@@ -304,7 +311,9 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
       if (c + 1 < nchunks) load_g(cur, c + 1);
       else if (tile + 1 < ntiles) load_g(nxt, 0);
       // V window chunk: K-major [channel group][tap][16 B] (once per cell when the head is one chunk wide)
-      if (nchunks > 1 || tile == 0) {
+      uint8_t* const vhi = sVhi + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
+      uint8_t* const vlo = sVlo + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
+      if (tile == 0 || !v_resident) {
         constexpr int VIT = (TP * 8 + NT - 1) / NT;     // items per thread at the full chunk width
         float4 va[VIT], vb[VIT];
 #pragma unroll
@@ -327,8 +336,8 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
             const float x[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
             uint4 hi, lo;
             split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(sVhi + (g8 * TP + n) * 16) = hi;
-            *reinterpret_cast<uint4*>(sVlo + (g8 * TP + n) * 16) = lo;
+            *reinterpret_cast<uint4*>(vhi + (g8 * TP + n) * 16) = hi;
+            *reinterpret_cast<uint4*>(vlo + (g8 * TP + n) * 16) = lo;
           }
         }
       }
@@ -340,9 +349,9 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
         // dP (+)= Ghi Vhi^T + Glo Vhi^T + Ghi Vlo^T
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a0 = smem_u32(pass == 1 ? sGlo : sGhi);
-          const uint32_t b0 = smem_u32(pass == 2 ? sVlo : sVhi);
+          const uint32_t b0 = smem_u32(pass == 2 ? vlo : vhi);
           for (int ks = 0; ks < (wc >> 4); ++ks)
-            mma_f16_ss(tdP, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
+            if (!(NAF_BWD_EXP & 4)) mma_f16_ss(tdP, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
                        make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (c | pass | ks) != 0);
         }
         // dVw[:, chunk] (+)= P^T_hi Ghi + P^T_lo Ghi + P^T_hi Glo   (A = P^T MN-major, B = G seen MN-major: K = pixels)
@@ -352,7 +361,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
           const uint32_t b0 = smem_u32(pass == 2 ? sGlo : sGhi);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            mma_f16_ss(tdV + c * DVC, make_desc(a0 + ks * 2 * 2048, 2048, 128),
+            if (!(NAF_BWD_EXP & 1)) mma_f16_ss(tdV + c * DVC, make_desc(a0 + ks * 2 * 2048, 2048, 128),
                        make_desc(b0 + ks * 2 * 128, 128, 128 * 16), idesc_dv, (tile | pass | ks) != 0);
         }
         commit(&mbar);
@@ -411,7 +420,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
         const uint32_t b0 = smem_u32(pass == 2 ? sQlo : sQhi);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          mma_f16_ss(tdK, make_desc(a0 + ks * 2 * 2048, 2048, 128), make_desc(b0 + ks * 2 * 128, 128, 128 * 16),
+          if (!(NAF_BWD_EXP & 2)) mma_f16_ss(tdK, make_desc(a0 + ks * 2 * 2048, 2048, 128), make_desc(b0 + ks * 2 * 128, 128, 128 * 16),
                      idesc_dk, (tile | pass | ks) != 0);
       }
       commit(&mbar);
@@ -439,7 +448,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv) {
 
   // ================= window gradients: TMEM lane = tap; one vector atomic per 4 elements
   {
-    const bool live = row < K2;
+    const bool live = row < K2 && !(NAF_BWD_EXP & 8);
     const int t = live ? row / K : 0, u = live ? row - (row / K) * K : 0;
     const int64_t cell = int64_t(b * p.h + wy0 + t) * p.w + wx0 + u;
     uint32_t r[32];
@@ -476,10 +485,17 @@ int taps_pad(int K) { return (K * K + 15) / 16 * 16; }
 template <int TP>
 int launch_bwd_tc(const naf_xattn_bwd_params& p, cudaStream_t st) {
   auto kern = xattn_bwd_cell_tc_kernel<TP>;
-  cudaError_t e = ensure_dyn_smem(kern, BwdCfg<TP>::kSmem);
+  const int dv = p.C / p.heads;
+  // shared memory: K window + V region + Q, G chunk, T (hi / lo each).  The V region holds the whole value head
+  // when that fits beside the rest (K <= 7 always; K = 9 up to dv = 176), else one 64-channel chunk.
+  const int fixed = 2 * BwdCfg<TP>::kWin + 4 * PIXIMG + 2 * TIMG;
+  const int v_full = 2 * (dv / 8) * TP * 16;
+  const int v_resident = fixed + v_full <= 220 * 1024 ? 1 : 0;
+  const int smem = fixed + (v_resident ? v_full : 2 * BwdCfg<TP>::kWin);
+  cudaError_t e = ensure_dyn_smem(kern, smem);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn_bwd(cell-tc): smem opt-in failed: %s", cudaGetErrorString(e));
   const unsigned grid = unsigned(p.B) * p.h * p.w * p.heads;
-  kern<<<grid, NT, BwdCfg<TP>::kSmem, st>>>(p, p.Ho / p.h, p.Wo / p.w, p.C / p.heads);
+  kern<<<grid, NT, smem, st>>>(p, p.Ho / p.h, p.Wo / p.w, dv, v_resident);
   return check_launch("xattn_bwd_cell_tc");
 }
 
