@@ -46,3 +46,38 @@ def test_tap_tables_none_for_integer_ratios():
 def test_invalid_windows_raise(args):
     with pytest.raises(ValueError):
         taps.axis_taps(*args)
+
+
+# ---- the union-window formulation of naf_xattn_union.cu, on the host ---------------------------------
+@pytest.mark.parametrize("Ho,Wo,h,w,K", [(32, 32, 13, 13, 9), (30, 45, 7, 11, 3), (20, 22, 20, 22, 15), (36, 36, 9, 9, 7), (37, 41, 16, 18, 9)])
+def test_union_window_multiplicity_softmax_equals_tap_softmax(Ho, Wo, h, w, K):
+    """Dense attention of an 8 x 16 pixel tile against the rectangle of cells its windows touch, weighted by the
+    per-pixel tap multiplicities mr[y][i] * mc[x][j], equals softmax over the K*K taps (duplicated taps included):
+    the identity the union kernel computes, checked with the oracle's tables and its attention."""
+    rt, ct = O.tap_tables(Ho, Wo, h, w, K)
+    rs = np.random.RandomState(3)
+    D, C = 16, 5
+    q = torch.from_numpy(rs.standard_normal((1, D, Ho, Wo)).astype(np.float32)) * 2
+    k = torch.from_numpy(rs.standard_normal((1, D, h, w)).astype(np.float32))
+    v = torch.from_numpy(rs.standard_normal((1, C, h, w)).astype(np.float32))
+    want = O.cross_attention(q, k, v, 1, K)[0]                       # (C, Ho, Wo)
+    scale = D ** -0.5
+    worst_span = 0
+    for ty0 in range(0, Ho, 8):
+        for tx0 in range(0, Wo, 16):
+            ys, xs = np.arange(ty0, min(ty0 + 8, Ho)), np.arange(tx0, min(tx0 + 16, Wo))
+            i0, i1, j0, j1 = rt[ys].min(), rt[ys].max(), ct[xs].min(), ct[xs].max()
+            RH, RW = i1 - i0 + 1, j1 - j0 + 1
+            worst_span = max(worst_span, RH, RW)
+            ku = k[0, :, i0:i1 + 1, j0:j1 + 1].reshape(D, -1)       # (D, |U|)
+            vu = v[0, :, i0:i1 + 1, j0:j1 + 1].reshape(C, -1)
+            for y in ys:
+                mr = np.bincount(rt[y] - i0, minlength=RH)
+                for x in xs:
+                    mc = np.bincount(ct[x] - j0, minlength=RW)
+                    m = torch.from_numpy(np.outer(mr, mc).reshape(-1).astype(np.float32))
+                    s = (q[0, :, y, x] @ ku) * scale
+                    e = m * torch.exp(s - s[m > 0].max())
+                    got = (vu @ e) / e.sum()
+                    assert (got - want[:, y, x]).abs().max().item() <= 2e-6, (y, x)
+    assert worst_span <= 32      # the kernel's RMAX: tables built from NATTEN windows stay inside it
