@@ -385,30 +385,54 @@ conv128_tc_kernel(ConvParams p) {
   if (warp == MMA_WARP) tmem_dealloc(tmem, 128);
 }
 
-// Epilogue of one 16x8 tile for the pipelined kernels (4 warps, warp ew owns TMEM lanes = pixels
-// [32 ew, 32 ew + 32)): accumulator -> +bias -> GroupNorm partial sums -> per-warp transpose slab ->
-// stores of four 128-byte runs per instruction.  `tmem_acc` = accumulator base + this warp's lane offset.
-template <bool OUT16>
+// Sum of N per-lane values over the warp with N + log2(32 / N) - 1 shuffles instead of 5 N: at every step a lane
+// keeps one half of its values and hands the other half to its partner.  Afterwards the lanes with the low
+// log2(32 / N) bits clear hold value `idx` = the high bits of the lane number, in v[0].
+template <int N>
+__device__ __forceinline__ void warp_sum_transposed(float (&v)[N], int lane) {
+  int step = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const float send = up ? v[i] : v[i + n / 2];
+      const float keep = up ? v[i + n / 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+#pragma unroll
+  for (; step > 0; step >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], step);
+}
+
+// Epilogue of one 16x8 tile for the pipelined kernels.  NEPI = 128: 4 warps, warp ew owns TMEM lanes = pixels
+// [32 ew, 32 ew + 32) and all 128 channels; NEPI = 256: 8 warps, warp ew owns the lanes of quarter ew & 3 and the
+// 64 channels of half ew >> 2.  Accumulator -> +bias -> GroupNorm partial sums -> per-warp transpose slab ->
+// stores of four 128-byte (fp16: 64-byte) runs per instruction.  `tmem_acc` = accumulator base + this warp's lane offset.
+template <bool OUT16, int NEPI>
 __device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem_acc, uint64_t* bar_acc_free, int b,
                                               int y0, int x0, int tile, int ew, int lane, int et, uint8_t* my_stage,
                                               const uint8_t* warp_stage, const float* s_bias, float (*s_part)[16]) {
-  const int row = ew * 32 + lane;
+  constexpr int NR = NEPI == 256 ? 2 : 4;   // rounds of 32 channels per thread
+  const int q = ew & 3, ch = ew >> 2;
+  const int row = q * 32 + lane;
   const int sub = lane >> 3, piece = lane & 7;
   const uint64_t one2 = pack2(1.f, 1.f);
   const bool valid = (y0 + (row >> 3)) < p.H && (x0 + (row & 7)) < p.W;
-  const int ybase = y0 + ew * 4, xbase = x0 + sub;
+  const int ybase = y0 + q * 4, xbase = x0 + sub;
   const int64_t oelem = ((int64_t(b) * p.H + ybase) * p.W + xbase) * p.out_pix_stride + p.out_ch_off + piece * 4;
   float* obase = static_cast<float*>(p.out) + oelem;          // fp32 view
   __half* obase_h = static_cast<__half*>(p.out) + oelem;      // fp16 view (OUT16)
-  uint64_t st2[16];   // [group][sum | sumsq], each as an (even, odd) channel pair
+  uint64_t st2[NR * 4];   // [group][sum | sumsq], each as an (even, odd) channel pair
 #pragma unroll
-  for (int j = 0; j < 16; ++j) st2[j] = 0ull;
+  for (int j = 0; j < NR * 4; ++j) st2[j] = 0ull;
 #pragma unroll
-  for (int rd = 0; rd < 4; ++rd) {
+  for (int rr = 0; rr < NR; ++rr) {
+    const int rd = ch * NR + rr;
     uint32_t r[32];
     tmem_ld32(tmem_acc + rd * 32, r);
     wait_ld();
-    if (rd == 3) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
+    if (rr == NR - 1) {   // the accumulator is in registers: the MMA of tile it+2 may overwrite it
       fence_before_sync();
       mbar_arrive(bar_acc_free);
     }
@@ -418,7 +442,7 @@ __device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem
       const float4 bv = *reinterpret_cast<const float4*>(&s_bias[rd * 32 + j]);
       const uint64_t o01 = fma2(pack2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])), one2, pack2(bv.x, bv.y));
       const uint64_t o23 = fma2(pack2(__uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])), one2, pack2(bv.z, bv.w));
-      const int g = rd * 2 + (j >> 4);
+      const int g = rr * 2 + (j >> 4);
       st2[g * 2] = fma2(o01, one2, st2[g * 2]);
       st2[g * 2] = fma2(o23, one2, st2[g * 2]);
       st2[g * 2 + 1] = fma2(o01, o01, st2[g * 2 + 1]);
@@ -452,15 +476,18 @@ __device__ __forceinline__ void ws_drain_tile(const ConvParams& p, uint32_t tmem
     }
   }
   if (p.part) {
+    constexpr int NV = NR * 4;
+    float v[NV];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < NV; ++j) {
       float v0, v1;
       unpack2(st2[j], v0, v1);
-      float v = valid ? v0 + v1 : 0.f;
-      v = warp_sum(v);
-      if (lane == 0) s_part[ew][j] = v;
+      v[j] = valid ? v0 + v1 : 0.f;
     }
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    warp_sum_transposed<NV>(v, lane);
+    if ((lane & (32 / NV - 1)) == 0) s_part[q][ch * NV + lane / (32 / NV)] = v[0];
+    if constexpr (NEPI == 256) asm volatile("bar.sync 2, 256;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
     if (et < 16)
       p.part[int64_t(tile) * 16 + et] = (s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et]);
   }
@@ -481,16 +508,23 @@ namespace {
 #ifndef NAF_CONV_NPROD
 #define NAF_CONV_NPROD 256
 #endif
-constexpr int WS_NPROD = NAF_CONV_NPROD, WS_NEPI = 128;   // producer threads: 256 or 384
+#ifndef NAF_CONV_NEPI
+#define NAF_CONV_NEPI 128   // epilogue threads of the conv layers: 128 (a thread drains a pixel's 128 channels) or
+#endif                      // 256 (two threads per pixel, 64 channels each; measured 5 - 12 % slower: 18 warps cap the
+                            // kernel at 96 registers and the layer is bound by shared-memory bandwidth, not by this group)
+constexpr int WS_NPROD = NAF_CONV_NPROD, WS_NEPI = 128;   // producer threads: 256 or 384; epilogue threads of the stem
 constexpr int WS_PXS = WS_NPROD / 16;                      // halo pixels converted concurrently
 constexpr int WS_THREADS = WS_NPROD + WS_NEPI + 64;
 constexpr int WS_MMA_WARP = (WS_NPROD + WS_NEPI) / 32;
+constexpr int WC_NEPI = NAF_CONV_NEPI;                     // conv layers
+constexpr int WC_THREADS = WS_NPROD + WC_NEPI + 64;
+constexpr int WC_MMA_WARP = (WS_NPROD + WC_NEPI) / 32;
 
 template <int KS>
 struct WsConvCfg {
   using Base = ConvCfg<KS, 1>;
   static constexpr int A_BUF = (Base::A_PLANE + 127) / 128 * 128;
-  static constexpr int STAGE = WS_NEPI * STAGE_SLOT;
+  static constexpr int STAGE = WC_NEPI * STAGE_SLOT;
   static constexpr int W_OFF = 2 * A_BUF;
 #ifndef NAF_CONV_WSLOTS
 #define NAF_CONV_WSLOTS 3
@@ -513,7 +547,7 @@ struct TileCtx {
 }  // namespace
 
 template <int KS, bool IN16, bool OUT16>
-__global__ void __launch_bounds__(WS_THREADS, 1)
+__global__ void __launch_bounds__(WC_THREADS, 1)
 conv128_ws_kernel(ConvParams p) {
   using Cfg = ConvCfg<KS, 1>;
   constexpr int ES = IN16 ? 2 : 4;              // bytes per input activation element
@@ -535,13 +569,13 @@ conv128_ws_kernel(ConvParams p) {
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int total = p.B * tiles_per_img;
 
-  if (warp == WS_MMA_WARP) tmem_alloc(&tmem_base_s, 256);
+  if (warp == WC_MMA_WARP) tmem_alloc(&tmem_base_s, 256);
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_a_full[s], WS_NPROD);
       mbar_init(&bar_a_free[s], 1);
       mbar_init(&bar_acc_full[s], 1);
-      mbar_init(&bar_acc_free[s], WS_NEPI);
+      mbar_init(&bar_acc_free[s], WC_NEPI);
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(&bar_w_full[s], 1);
@@ -551,7 +585,7 @@ conv128_ws_kernel(ConvParams p) {
   }
   if (tid < CC) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
   // global element offset of halo pixel px relative to the tile's halo origin (same for every tile)
-  for (int px = tid; px < Ws::NIT * WS_PXS; px += WS_THREADS) {
+  for (int px = tid; px < Ws::NIT * WS_PXS; px += WC_THREADS) {
     const int q = px < HP ? px : HP - 1, hy = q / WX, hx = q - hy * WX;
     s_goff[px] = (hy * p.W + hx) * CC;
   }
@@ -728,13 +762,13 @@ conv128_ws_kernel(ConvParams p) {
       mbar_arrive(&bar_a_full[buf]);
       cur = nxt;
     }
-  } else if (warp < WS_MMA_WARP) {
+  } else if (warp < WC_MMA_WARP) {
     // =============================================================================== EPILOGUE
-    // warp ew owns TMEM lanes (pixels) [32 ew, 32 ew + 32); a thread drains its pixel's 128 channels
-    // in 4 rounds of 32 columns, each round transposed through the warp's private smem slab so that
-    // every store instruction writes four 128-byte runs (4 pixels x 32 channels).
+    // warp ew owns TMEM lanes (pixels) [32 (ew & 3), +32) and, with 8 epilogue warps, the 64 channels of half
+    // ew >> 2; a thread drains its channels in rounds of 32 columns, each round transposed through the warp's
+    // private smem slab so that every store instruction writes four 128-byte runs (4 pixels x 32 channels).
     const int ew = warp - WS_NPROD / 32, et = tid - WS_NPROD;
-    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t lane_off = uint32_t((ew & 3) * 32) << 16;
     uint8_t* my_stage = sStage + et * STAGE_SLOT;
     const uint8_t* warp_stage = sStage + ew * 32 * STAGE_SLOT;
     int it = 0;
@@ -745,10 +779,10 @@ conv128_ws_kernel(ConvParams p) {
       const int y0 = ty * TH, x0 = tx * TW;
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      ws_drain_tile<OUT16>(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, y0, x0, tile, ew, lane, et, my_stage,
+      ws_drain_tile<OUT16, WC_NEPI>(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, y0, x0, tile, ew, lane, et, my_stage,
                            warp_stage, s_bias, s_part[buf]);
     }
-  } else if (warp == WS_MMA_WARP) {
+  } else if (warp == WC_MMA_WARP) {
     // ============================================================================= MMA ISSUER
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, CC, false, false);
@@ -820,7 +854,7 @@ conv128_ws_kernel(ConvParams p) {
 
   fence_before_sync();
   __syncthreads();
-  if (warp == WS_MMA_WARP) tmem_dealloc(tmem, 256);
+  if (warp == WC_MMA_WARP) tmem_dealloc(tmem, 256);
 }
 
 // ---- stem on the tensor core (1 pass): Conv2d(3 -> 128, KS, reflect) as a 128 x 128 x {16, 32} GEMM ----
@@ -942,7 +976,7 @@ stem_tc_kernel(ConvParams p, const float* __restrict__ image, int64_t sb, int64_
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       mbar_wait(&bar_acc_full[buf], (it >> 1) & 1);
       fence_after_sync();
-      ws_drain_tile<OUT16>(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, ty * TH, tx * TW, tile, ew, lane, et,
+      ws_drain_tile<OUT16, WS_NEPI>(p, tmem + lane_off + buf * CC, &bar_acc_free[buf], b, ty * TH, tx * TW, tile, ew, lane, et,
                            my_stage, warp_stage, s_bias, s_part[buf]);
     }
   } else if (warp == WS_MMA_WARP) {
@@ -1136,7 +1170,7 @@ int launch_conv_ws(const ConvParams& p, cudaStream_t st) {
   const int sms = device_sm_count();
   const int64_t total = int64_t(p.B) * p.tiles_y * p.tiles_x;
   const int grid = int(total < sms ? total : sms);
-  kern<<<grid, WS_THREADS, Ws::SMEM, st>>>(p);
+  kern<<<grid, WC_THREADS, Ws::SMEM, st>>>(p);
   return check_launch("enc_conv(ws)");
 }
 

@@ -48,7 +48,17 @@ constexpr int NFRONT = 256, NBACK = 256, NTHREADS = NFRONT + NBACK + 64;
 constexpr int MMA_WARP = (NFRONT + NBACK) / 32, LOAD_WARP = MMA_WARP + 1;
 #ifndef NAF_TMA_EXP
 #define NAF_TMA_EXP 0   // profiling variants (scripts/build_variant.py): 1 = no output stores, 2 = no q loads,
-#endif                  // 4 = softmax without the exponentials (P = 1 on the valid taps), 8 = constant cos/sin (no table loads)
+#endif                  // 4 = softmax without the exponentials (P = 1 on the valid taps), 8 = constant cos/sin (no table loads),
+                        // 16 = P V without the Plo * Vhi pass
+#ifndef NAF_TMA_NOB
+#define NAF_TMA_NOB 1   // accumulator buffers in TMEM for the wide value heads.  2 = the head is accumulated in parts of
+#endif                  // 96 (dv 192) or 64 (dv 256) columns alternating between two buffers, so that the drain of one part
+                        // overlaps the P V of the next: measured SLOWER (pipeline alone 2.52 -> 3.08 ms at C2, 3.94 -> 5.16 ms
+                        // at C3, profiles/r3_tma_experiments.txt).  A tcgen05.mma whose A operand lives in TMEM costs
+                        // about 64 clocks however narrow N is, so halving N doubles the tensor time of P V.
+#ifndef NAF_TMA_QPF
+#define NAF_TMA_QPF 0   // L2 prefetch of the query rows, in tiles ahead of the register loads (0 = none: measured
+#endif                  // neutral at 3 tiles, -5 % at 6: the loads are not what the front group waits for)
 constexpr int kSmemLimit = 227 * 1024 - 1024;   // dynamic shared memory we allow ourselves (static barriers extra)
 
 template <int TP>
@@ -56,8 +66,9 @@ struct TmaWindowOf { static constexpr int K = TP == 16 ? 3 : TP == 32 ? 5 : TP =
 
 constexpr int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
-// TP: padded taps; DVH: value channels per accumulator half; NH: halves; ROUNDS: staging rounds per half
-template <int TP, int DVH, int NH, int ROUNDS>
+// TP: padded taps; DVH: value channels per accumulator part; NH: parts per tile; ROUNDS: staging rounds per part;
+// NOB: accumulator buffers in TMEM (2: the drain of part n overlaps the P V of part n+1)
+template <int TP, int DVH, int NH, int ROUNDS, int NOB = 1>
 struct TmaCfg {
   static constexpr int K = TmaWindowOf<TP>::K, K2 = K * K;
   static constexpr int DV = DVH * NH;
@@ -89,13 +100,14 @@ struct TmaCfg {
   static constexpr int kSmemBytes = kOffMx + kMx;
   // (the row sums travel through shared memory, not TMEM: 128 + 2*128 + 128 columns is exactly 512, which gives
   // the 11x11 / dv 256 configuration its second Q stage)
-  static constexpr int kQStages = (128 + 2 * TP + DVH <= 512) ? 2 : 1;
+  static constexpr int kQStages = (128 + 2 * TP + NOB * DVH <= 512) ? 2 : 1;
   static constexpr int kTmemQ = 0;
   static constexpr int kTmemS = 64 * kQStages;
   static constexpr int kTmemO = kTmemS + 2 * TP;
-  static constexpr int kTmemUsed = kTmemO + DVH;
+  static constexpr int kTmemUsed = kTmemO + NOB * DVH;
   static constexpr bool kFits = kTmemUsed <= 512 && kSmemBytes <= kSmemLimit && (DVH % ROUNDS) == 0 &&
-                                (kRoundCols % 32) == 0 && DVH % 16 == 0 && DVH <= 256 && DV / 8 <= 256;
+                                (kRoundCols % 32) == 0 && DVH % 16 == 0 && DVH <= 256 && DV / 8 <= 256 &&
+                                (NOB == 1 || (NOB == 2 && DVH <= 128));
 };
 
 __device__ __forceinline__ uint64_t tm_pack2(float a, float b) {
@@ -146,6 +158,8 @@ struct TmGeom {
   int th_last;         // rows of the last tile
   int n_items;
   int groups_k, groups_v;   // channel groups per (batch, plane) of the K / V plane tensors: D/8, C/8
+  int tab_bytes;            // RoPE table rows of one cell staged in shared memory per K window buffer
+                            // ([cos_y | sin_y] rh rows, [cos_x | sin_x] rw rows, 64 B each); 0 = read them from global
 };
 
 }  // namespace
@@ -191,15 +205,15 @@ kv_planes_kernel(const T* __restrict__ src, uint4* __restrict__ dst, int B, int 
 }
 
 // 18 warps: one SM sub-partition (16 K registers) hosts 5 of them, hence at most 96 registers per thread
-template <int TP, int DVH, int NH, int ROUNDS>
+template <int TP, int DVH, int NH, int ROUNDS, int NOB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
                       const __grid_constant__ CUtensorMap tmO2) {
-  using Cfg = TmaCfg<TP, DVH, NH, ROUNDS>;
+  using Cfg = TmaCfg<TP, DVH, NH, ROUNDS, NOB>;
   constexpr int K = Cfg::K, K2 = Cfg::K2;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_o_full, bar_o_free;
+  __shared__ uint64_t bar_q_full[2], bar_s_full[2], bar_p_full[2], bar_o_full[2], bar_o_free[2];
   __shared__ uint64_t bar_k_full[2], bar_k_free[2], bar_v_full[2], bar_v_free[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -208,6 +222,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
   uint8_t* const stage_out = smem + Cfg::kOffStage;
   float* const mx = reinterpret_cast<float*>(smem + Cfg::kOffMx);   // [tile parity][half][row]
   float* const lsum = mx + 2 * 2 * 128;                             // [tile & 3][half][row]
+  const float* const sTab = reinterpret_cast<const float*>(smem + Cfg::kSmemBytes);   // [K buffer][tab_bytes]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rh = gm.rh, rw = gm.rw;
@@ -224,12 +239,14 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
       mbar_init(&bar_s_full[s], 1);
       mbar_init(&bar_p_full[s], NFRONT);
       mbar_init(&bar_k_full[s], 1);
-      mbar_init(&bar_k_free[s], 1);
+      mbar_init(&bar_k_free[s], gm.tab_bytes ? 1 + NFRONT / 32 : 1);   // MMA commit (+ the front warps: table rows)
       mbar_init(&bar_v_full[s], 1);
       mbar_init(&bar_v_free[s], 1);
     }
-    mbar_init(&bar_o_full, 1);
-    mbar_init(&bar_o_free, NBACK);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_o_full[s], 1);
+      mbar_init(&bar_o_free[s], NBACK);
+    }
     fence_mbar_init();
   }
   // zero the tails the MMAs over-read behind every window plane (never written afterwards)
@@ -261,24 +278,49 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     const float qscale = p.scale * 1.4426950408889634f;
 
     float qa[P], qb[P];
-    int q_y = 0, q_x = 0;
+    const bool tabs = gm.tab_bytes != 0;
+    // of the q in the registers: its table rows (tables in shared memory: row / column inside the cell; tables
+    // in global memory: the target pixel) and bit 0: first tile of the item, 1: last tile, 2: K buffer, 3: its parity
+    int q_r = 0, q_c = 0, q_flags = 0;
 
-    int f_g = 0;   // issue_q is called for g = 0, 1, 2, ... in order
-    auto issue_q = [&]() {
-      const int g = f_g++;
-      const int it_seq = tm_div(g, dv.ntiles), tile = g - it_seq * ntiles;
+    // element offset of this thread's query half row for tile g (clamped to the tile's last pixel)
+    auto q_offset = [&](int g, int& it_seq, int& tile, int& ly, int& lx, int& y, int& x) -> int64_t {
+      it_seq = tm_div(g, dv.ntiles);
+      tile = g - it_seq * ntiles;
       const TmItem it = item_of(it_seq);
       int pi = tile * tile_rows + row;
       const int lim = min(npix, (tile + 1) * tile_rows);
       if (pi >= lim) pi = lim - 1;
-      const int py = tm_div(pi, dv.rw);
-      q_y = it.ci * rh + py;
-      q_x = it.cj * rw + (pi - py * rw);
-      const int64_t qoff = int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
-                           int64_t(tm_div(q_y, dv.rep_y)) * p.q_stride_y + int64_t(tm_div(q_x, dv.rep_x)) * p.q_stride_x;
+      ly = tm_div(pi, dv.rw);
+      lx = pi - ly * rw;
+      y = it.ci * rh + ly;
+      x = it.cj * rw + lx;
+      return int64_t(it.b) * p.q_stride_b + it.head * DQ + P * half +
+             int64_t(tm_div(y, dv.rep_y)) * p.q_stride_y + int64_t(tm_div(x, dv.rep_x)) * p.q_stride_x;
+    };
+
+    int f_g = 0;   // issue_q is called for g = 0, 1, 2, ... in order
+    auto issue_q = [&]() {
+      const int g = f_g++;
+#if NAF_TMA_QPF > 0
+      // Under the output stream an HBM read takes several microseconds; the register prefetch covers one
+      // tile.  Pull the lines of tile g + NAF_TMA_QPF into L2 now: the two threads of a row cover the two
+      // 128-byte lines of the head's query row (one line for bf16).
+      if (g + NAF_TMA_QPF < total_tiles && !(NAF_TMA_EXP & 2)) {
+        int a, b, c, d, e, f;
+        const int64_t off = q_offset(g + NAF_TMA_QPF, a, b, c, d, e, f) + (half ? HALF : 0);
+        prefetch_l2(q_bf16 ? static_cast<const void*>(reinterpret_cast<const __nv_bfloat16*>(p.q) + off)
+                           : static_cast<const void*>(p.q + off));
+      }
+#endif
+      int seq, tile, ly, lx, y, x;
+      const int64_t qoff = q_offset(g, seq, tile, ly, lx, y, x);
+      q_r = tabs ? ly : y;
+      q_c = tabs ? lx : x;
+      q_flags = int(tile == 0) | (int(tile + 1 == ntiles) << 1) | ((seq & 3) << 2);
 #if NAF_TMA_EXP & 2
 #pragma unroll
-      for (int j = 0; j < P; ++j) { qa[j] = 0.01f * float(j + (pi & 7)); qb[j] = -0.02f * float(j); }
+      for (int j = 0; j < P; ++j) { qa[j] = 0.01f * float(j + (lx & 7)); qb[j] = -0.02f * float(j); }
       (void)qoff;
 #else
       if (q_bf16) {
@@ -302,18 +344,31 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     constexpr int QS = Cfg::kQStages;
     auto stage_q = [&](int g) {   // g: the tile whose q is in the registers
       if (rope) {
-        const float* ct = half == 0 ? p.cos_y + int64_t(q_y) * P : p.cos_x + int64_t(q_x) * P;
-        const float* st = half == 0 ? p.sin_y + int64_t(q_y) * P : p.sin_x + int64_t(q_x) * P;
         float c[P], sn[P];
 #if NAF_TMA_EXP & 8
 #pragma unroll
         for (int j = 0; j < P; ++j) { c[j] = 0.8f; sn[j] = 0.6f; }
-        (void)ct; (void)st;
 #else
-        ldg8(ct, *reinterpret_cast<float(*)[8]>(&c[0]));
-        ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
-        ldg8(st, *reinterpret_cast<float(*)[8]>(&sn[0]));
-        ldg8(st + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+        if (tabs) {
+          // the cell's table rows came with its K window (same buffer index, same barrier)
+          const int kb = (q_flags >> 2) & 1;
+          if (q_flags & 1) mbar_wait(&bar_k_full[kb], (q_flags >> 3) & 1);
+          const float* tb = sTab + kb * (gm.tab_bytes / 4);
+          const float* ct = half == 0 ? tb + q_r * P : tb + 2 * rh * P + q_c * P;
+          const float* st = ct + (half == 0 ? rh : rw) * P;
+#pragma unroll
+          for (int j = 0; j < P; j += 4) {
+            *reinterpret_cast<float4*>(&c[j]) = *reinterpret_cast<const float4*>(ct + j);
+            *reinterpret_cast<float4*>(&sn[j]) = *reinterpret_cast<const float4*>(st + j);
+          }
+        } else {
+          const float* ct = half == 0 ? p.cos_y + int64_t(q_r) * P : p.cos_x + int64_t(q_c) * P;
+          const float* st = half == 0 ? p.sin_y + int64_t(q_r) * P : p.sin_x + int64_t(q_c) * P;
+          ldg8(ct, *reinterpret_cast<float(*)[8]>(&c[0]));
+          ldg8(ct + 8, *reinterpret_cast<float(*)[8]>(&c[8]));
+          ldg8(st, *reinterpret_cast<float(*)[8]>(&sn[0]));
+          ldg8(st + 8, *reinterpret_cast<float(*)[8]>(&sn[8]));
+        }
 #endif
         const uint64_t qs2 = tm_pack2(qscale, qscale);
 #pragma unroll
@@ -345,6 +400,11 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
       wait_st();
       fence_before_sync();
       mbar_arrive(&bar_q_full[QS == 2 ? (g & 1) : 0]);
+      if (tabs && (q_flags & 2)) {
+        // last tile of the item: this warp has read its table rows, the buffer may be refilled
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_k_free[(q_flags >> 2) & 1]);
+      }
     };
 
     if (total_tiles > 0) {
@@ -485,7 +545,10 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         float inv_l = 0.f;
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh, ++n) {
-          mbar_wait(&bar_o_full, n & 1);
+          const int ob = NOB == 2 ? (n & 1) : 0;                 // accumulator buffer of this part
+          const int opar = NOB == 2 ? ((n >> 1) & 1) : (n & 1);   // ... and the parity of this use
+          const uint32_t tO = tmem + Cfg::kTmemO + ob * DVH + lane_off;
+          mbar_wait(&bar_o_full[ob], opar);
           fence_after_sync();
           if (hh == 0) {
             inv_l = 1.f / (lsum[((g & 3) * 2) * 128 + row] + lsum[((g & 3) * 2 + 1) * 128 + row]);
@@ -502,18 +565,17 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
             for (int rd = 0; rd < ROUNDS; ++rd)
 #pragma unroll
               for (int c = 0; c < HC; c += 16)
-                tmem_ld16(tmem + Cfg::kTmemO + lane_off + rd * RC + half * HC + c,
-                          *reinterpret_cast<uint32_t(*)[16]>(&pre[rd * HC + c]));
+                tmem_ld16(tO + rd * RC + half * HC + c, *reinterpret_cast<uint32_t(*)[16]>(&pre[rd * HC + c]));
             wait_ld();
             fence_before_sync();
-            mbar_arrive(&bar_o_free);
+            mbar_arrive(&bar_o_free[ob]);
           }
 #pragma unroll
           for (int rd = 0; rd < ROUNDS; ++rd, ++rc) {
             // Staging slot of this round.  With two slots nobody waits here: the stores that last read this
             // slot (round rc-2) were waited for by the issuer before the barrier of round rc-1.
             uint8_t* const slot = stage_out + (Cfg::NSTG == 2 ? (rc & 1) * Cfg::kSlot : 0);
-            const uint32_t to = tmem + Cfg::kTmemO + lane_off + rd * RC + half * HC;
+            const uint32_t to = tO + rd * RC + half * HC;
             const uint64_t inv2 = tm_pack2(inv_l, inv_l);
             // normalise 16 accumulator columns and write them into the swizzled box images
             auto stage16 = [&](const uint32_t* r, int c) {
@@ -556,7 +618,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
                 else if (rd == ROUNDS - 1) {
                   // the whole accumulator has left TMEM: the next PV may overwrite O
                   fence_before_sync();
-                  mbar_arrive(&bar_o_free);
+                  mbar_arrive(&bar_o_free[ob]);
                 }
                 stage16(r[c & 1], c * 16);
               }
@@ -591,7 +653,15 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         const int wy0 = window_origin(it.ci, p.h, K), wx0 = window_origin(it.cj, p.w, K);
         const int kb = it_seq & 1;
         if (it_seq >= 2) mbar_wait(&bar_k_free[kb], ((it_seq >> 1) - 1) & 1);
-        mbar_expect_tx(&bar_k_full[kb], 2 * Cfg::kKPlane);
+        mbar_expect_tx(&bar_k_full[kb], 2 * Cfg::kKPlane + gm.tab_bytes);
+        if (gm.tab_bytes) {
+          float* tb = const_cast<float*>(sTab) + kb * (gm.tab_bytes / 4);
+          constexpr int P = DQ / 4;
+          bulk_load(tb, p.cos_y + int64_t(it.ci) * rh * P, rh * P * 4, &bar_k_full[kb]);
+          bulk_load(tb + rh * P, p.sin_y + int64_t(it.ci) * rh * P, rh * P * 4, &bar_k_full[kb]);
+          bulk_load(tb + 2 * rh * P, p.cos_x + int64_t(it.cj) * rw * P, rw * P * 4, &bar_k_full[kb]);
+          bulk_load(tb + (2 * rh + rw) * P, p.sin_x + int64_t(it.cj) * rw * P, rw * P * 4, &bar_k_full[kb]);
+        }
         uint8_t* kdst = sK + kb * Cfg::kKWin;
         const int gk = (it.b * 2) * gm.groups_k + it.head * KC;
         tmap::load4(kdst, &tmK, 0, wx0, wy0, gk, &bar_k_full[kb]);
@@ -612,7 +682,6 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, TP, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, DVH, false, true);
-      const uint32_t tO = tmem + Cfg::kTmemO;
       constexpr int QS = Cfg::kQStages;
       int qk_seq = 0, qk_tile = 0, pv_seq = 0, pv_tile = 0;   // (item, tile) of the next QK / PV
       int n = 0;                                              // accumulator uses issued so far
@@ -658,11 +727,14 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         const uint32_t tP = tmem + Cfg::kTmemS + s * TP;
 #pragma unroll
         for (int hh = 0; hh < NH; ++hh, ++n) {
-          mbar_wait(&bar_o_free, (n + 1) & 1);   // O drained by the epilogue of the previous use
+          const int ob = NOB == 2 ? (n & 1) : 0;
+          const uint32_t tO = tmem + Cfg::kTmemO + ob * DVH;
+          mbar_wait(&bar_o_free[ob], ((NOB == 2 ? (n >> 1) : n) + 1) & 1);   // drained by the epilogue of the previous use
           fence_after_sync();
           // O = Phi*Vhi + Plo*Vhi + Phi*Vlo on the channel groups of this half
 #pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
+            if ((NAF_TMA_EXP & 16) && pass == 1) continue;   // profiling: two-pass P V
             const uint32_t a0 = tP + (pass == 1 ? TP / 2 : 0);
             const uint32_t b0 = smem_u32(w + (pass == 2 ? Cfg::kVStride : 0) + hh * (DVH / 8) * (K2 * 16));
 #pragma unroll
@@ -672,7 +744,7 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
               mma_f16_ts(tO, a0 + kk * 8, db, idesc_pv, (pass | kk) != 0);
             }
           }
-          commit(&bar_o_full);
+          commit(&bar_o_full[ob]);
         }
         if (last_of_item) commit(&bar_v_free[vb]);
       };
@@ -726,16 +798,13 @@ size_t tm_workspace_bytes(const naf_xattn_params& p) {
   return size_t(p.B) * p.h * p.w * (size_t(p.D) + p.C) * 4 + 256;
 }
 
-template <int TP, int DVH, int NH, int ROUNDS>
+template <int TP, int DVH, int NH, int ROUNDS, int NOB>
 int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
-  using Cfg = TmaCfg<TP, DVH, NH, ROUNDS>;
+  using Cfg = TmaCfg<TP, DVH, NH, ROUNDS, NOB>;
   if constexpr (!Cfg::kFits) {
-    return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): tile %dx%dx%d/%d does not fit", TP, DVH, NH, ROUNDS);
+    return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): tile %dx%dx%d/%d/%d does not fit", TP, DVH, NH, ROUNDS, NOB);
   } else {
-    auto kern = xattn_cell_tma_kernel<TP, DVH, NH, ROUNDS>;
-    cudaError_t e = ensure_dyn_smem(kern, Cfg::kSmemBytes);
-    if (e != cudaSuccess)
-      return fail(NAF_ERR_CUDA, "xattn(cell-tma): smem opt-in failed: %s", cudaGetErrorString(e));
+    auto kern = xattn_cell_tma_kernel<TP, DVH, NH, ROUNDS, NOB>;
     const int sms = device_sm_count();
     TmGeom gm;
     gm.rh = p.Ho / p.h;
@@ -745,6 +814,13 @@ int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
     gm.n_items = int(items);
     gm.groups_k = p.D / 8;
     gm.groups_v = p.C / 8;
+    // RoPE table rows of a cell in shared memory (one set per K window buffer) when there is room for them
+    gm.tab_bytes = p.cos_y ? 2 * (gm.rh + gm.rw) * (DQ / 4) * 4 : 0;
+    if (Cfg::kSmemBytes + Cfg::NKB * gm.tab_bytes > kSmemLimit) gm.tab_bytes = 0;
+    const int smem_bytes = Cfg::kSmemBytes + Cfg::NKB * gm.tab_bytes;
+    const cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
+    if (e != cudaSuccess)
+      return fail(NAF_ERR_CUDA, "xattn(cell-tma): smem opt-in failed: %s", cudaGetErrorString(e));
     TmDivs dv;
     dv.ntiles = tm_make_div(uint32_t(gm.ntiles));
     dv.heads = tm_make_div(uint32_t(p.heads));
@@ -799,14 +875,14 @@ int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
         return fail(NAF_ERR_CUDA, "xattn(cell-tma): cuTensorMapEncodeTiled failed");
     }
     const int grid = int(items < sms ? items : sms);
-    kern<<<grid, NTHREADS, Cfg::kSmemBytes, st>>>(p, gm, dv, tmK, tmV, tmO, tmO2);
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(p, gm, dv, tmK, tmV, tmO, tmO2);
     return check_launch("xattn_cell_tma");
   }
 }
 
 // (value head dim) -> (DVH, NH, ROUNDS) per padded tap count; 0 = no configuration
 struct TmPlan {
-  int dvh = 0, nh = 0, rounds = 0;
+  int dvh = 0, nh = 0, rounds = 0, nob = 1;
 };
 
 template <int TP>
@@ -819,14 +895,17 @@ constexpr TmPlan tm_plan(int dv, bool bf16) {
     case 64: if (TmaCfg<TP, 64, 1, 1>::kFits) pl = {64, 1, 1}; break;
     case 96: if (!bf16 && TmaCfg<TP, 96, 1, 1>::kFits) pl = {96, 1, 1}; break;
     case 128: if (TmaCfg<TP, 128, 1, 2>::kFits) pl = {128, 1, 2}; break;
+    // (NAF_TMA_NOB == 2: two accumulator buffers of narrower parts -- a measured-slower build option, see above)
     case 192:
-      if (bf16) { if (TmaCfg<TP, 192, 1, 1>::kFits) pl = {192, 1, 1}; }
-      else if (TmaCfg<TP, 192, 1, 2>::kFits) pl = {192, 1, 2};
+      if (bf16) { if (TmaCfg<TP, 192, 1, 1>::kFits) pl = {192, 1, 1, 1}; }
+      else if (NAF_TMA_NOB == 2 && TmaCfg<TP, 96, 2, 1, 2>::kFits) pl = {96, 2, 1, 2};
+      else if (TmaCfg<TP, 192, 1, 2>::kFits) pl = {192, 1, 2, 1};
       break;
     case 256:
-      if (TmaCfg<TP, 256, 1, 4>::kFits) pl = {256, 1, 4};
-      else if (bf16) { if (TmaCfg<TP, 128, 2, 2>::kFits) pl = {128, 2, 2}; }
-      else if (TmaCfg<TP, 128, 2, 4>::kFits) pl = {128, 2, 4};
+      if (!bf16 && NAF_TMA_NOB == 2 && TmaCfg<TP, 64, 4, 2, 2>::kFits) pl = {64, 4, 2, 2};
+      else if (TmaCfg<TP, 256, 1, 4>::kFits) pl = {256, 1, 4, 1};
+      else if (bf16) { if (TmaCfg<TP, 128, 2, 2>::kFits) pl = {128, 2, 2, 1}; }
+      else if (TmaCfg<TP, 128, 2, 4>::kFits) pl = {128, 2, 4, 1};
       break;
     default: break;
   }
@@ -850,7 +929,7 @@ int launch_tma_plan(const naf_xattn_params& p, cudaStream_t st) {
   if constexpr (pl.dvh == 0) {
     return fail(NAF_ERR_UNSUPPORTED, "xattn(cell-tma): no plan for dv=%d", DVFULL);
   } else {
-    return launch_tma<TP, pl.dvh, pl.nh, pl.rounds>(p, st);
+    return launch_tma<TP, pl.dvh, pl.nh, pl.rounds, pl.nob>(p, st);
   }
 }
 
