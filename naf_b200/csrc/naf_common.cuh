@@ -111,6 +111,12 @@ __device__ __forceinline__ void ldg_stream8(const float* p, float (&r)[8]) {
                  "=f"(r[7])
                : "l"(p));
 }
+__device__ __forceinline__ void ldg_hint8(const float* p, float (&r)[8], uint64_t policy) {
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]),
+                 "=f"(r[7])
+               : "l"(p), "l"(policy));
+}
 __device__ __forceinline__ void ldg8(const float* p, float (&r)[8]) {
   asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]),

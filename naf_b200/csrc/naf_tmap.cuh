@@ -66,6 +66,24 @@ __device__ __forceinline__ void store4(const CUtensorMap* m, int c0, int c1, int
                : "memory");
 }
 
+// the same with an L2 cache-policy operand (createpolicy.fractional.L2::evict_first / evict_last)
+__device__ __forceinline__ void store4_hint(const CUtensorMap* m, int c0, int c1, int c2, int c3, const void* ssrc,
+                                            uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(umma::smem_u32(ssrc)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
 // byte offset of 16-byte chunk `c` (0..7) of 128-byte row `row` inside a SWIZZLE_128B box image whose base
 // is 1024-byte aligned: the chunk index is XORed with the row index modulo 8
 __device__ __forceinline__ uint32_t swz128(uint32_t row, uint32_t c) { return row * 128u + ((c ^ (row & 7u)) << 4); }

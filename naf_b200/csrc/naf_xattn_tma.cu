@@ -56,6 +56,15 @@ constexpr int MMA_WARP = (NFRONT + NBACK) / 32, LOAD_WARP = MMA_WARP + 1;
                         // overlaps the P V of the next: measured SLOWER (pipeline alone 2.52 -> 3.08 ms at C2, 3.94 -> 5.16 ms
                         // at C3, profiles/r3_tma_experiments.txt).  A tcgen05.mma whose A operand lives in TMEM costs
                         // about 64 clocks however narrow N is, so halving N doubles the tensor time of P V.
+#ifndef NAF_TMA_QBULK
+#define NAF_TMA_QBULK 0   // bulk L2 prefetch of a cell's query rows by the loader warp, one item ahead (measured: C2 4.30 ->
+#endif                    // 4.55 ms, x at target resolution 4.97 -> 6.5 ms: the output stream evicts the rows before they are used)
+#ifndef NAF_TMA_STHINT
+#define NAF_TMA_STHINT 0  // L2 policy of the output tensor stores: 0 none, 1 evict_first, 2 evict_last
+#endif
+#ifndef NAF_TMA_QHINT
+#define NAF_TMA_QHINT 0   // 1 = evict_last policy on the query loads
+#endif
 #ifndef NAF_TMA_QPF
 #define NAF_TMA_QPF 0   // L2 prefetch of the query rows, in tiles ahead of the register loads (0 = none: measured
 #endif                  // neutral at 3 tiles, -5 % at 6: the loads are not what the front group waits for)
@@ -93,7 +102,7 @@ struct TmaCfg {
   static constexpr int NSTG = (kMin + kSlot <= kSmemLimit) ? 2 : 1;
   static constexpr int kStage = NSTG * kSlot;
   static constexpr int NVB = (kMin + (NSTG - 1) * kSlot + kVWin <= kSmemLimit) ? 2 : 1;
-  static constexpr int kOffK = 0;
+  [[maybe_unused]] static constexpr int kOffK = 0;
   static constexpr int kOffV = NKB * kKWin;
   static constexpr int kOffStage = round_up(kOffV + NVB * kVWin, 1024);
   static constexpr int kOffMx = kOffStage + kStage;
@@ -101,7 +110,7 @@ struct TmaCfg {
   // (the row sums travel through shared memory, not TMEM: 128 + 2*128 + 128 columns is exactly 512, which gives
   // the 11x11 / dv 256 configuration its second Q stage)
   static constexpr int kQStages = (128 + 2 * TP + NOB * DVH <= 512) ? 2 : 1;
-  static constexpr int kTmemQ = 0;
+  [[maybe_unused]] static constexpr int kTmemQ = 0;
   static constexpr int kTmemS = 64 * kQStages;
   static constexpr int kTmemO = kTmemS + 2 * TP;
   static constexpr int kTmemUsed = kTmemO + NOB * DVH;
@@ -279,6 +288,9 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
 
     float qa[P], qb[P];
     const bool tabs = gm.tab_bytes != 0;
+#if NAF_TMA_QHINT
+    const uint64_t q_policy = tmap::policy_evict_last();
+#endif
     // of the q in the registers: its table rows (tables in shared memory: row / column inside the cell; tables
     // in global memory: the target pixel) and bit 0: first tile of the item, 1: last tile, 2: K buffer, 3: its parity
     int q_r = 0, q_c = 0, q_flags = 0;
@@ -332,10 +344,17 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         load8_as_float(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
       } else {
         const float* qp = p.q + qoff;
+#if NAF_TMA_QHINT
+        ldg_hint8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]), q_policy);
+        ldg_hint8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]), q_policy);
+        ldg_hint8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]), q_policy);
+        ldg_hint8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]), q_policy);
+#else
         ldg_stream8(qp, *reinterpret_cast<float(*)[8]>(&qa[0]));
         ldg_stream8(qp + 8, *reinterpret_cast<float(*)[8]>(&qa[8]));
         ldg_stream8(qp + HALF, *reinterpret_cast<float(*)[8]>(&qb[0]));
         ldg_stream8(qp + HALF + 8, *reinterpret_cast<float(*)[8]>(&qb[8]));
+#endif
       }
 #endif
     };
@@ -534,6 +553,11 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
       tmap::prefetch_desc(&tmO);
       tmap::prefetch_desc(&tmO2);
     }
+#if NAF_TMA_STHINT == 1
+    const uint64_t st_policy = tmap::policy_evict_first();
+#elif NAF_TMA_STHINT == 2
+    const uint64_t st_policy = tmap::policy_evict_last();
+#endif
     int n = 0;      // accumulator uses so far: (tile, half) pairs
     int g = 0;
     int rc = 0;     // staging rounds so far
@@ -633,7 +657,13 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
               const int per_box = bf16_out ? 64 : 32;
               const int nbox = RC / per_box;
               if (!(NAF_TMA_EXP & 1))
-                for (int j = 0; j < nbox; ++j) tmap::store4(tm, c0 + j * per_box, x0, y0, it.b, slot + j * Cfg::kBox);
+                for (int j = 0; j < nbox; ++j) {
+#if NAF_TMA_STHINT
+                  tmap::store4_hint(tm, c0 + j * per_box, x0, y0, it.b, slot + j * Cfg::kBox, st_policy);
+#else
+                  tmap::store4(tm, c0 + j * per_box, x0, y0, it.b, slot + j * Cfg::kBox);
+#endif
+                }
               bulk_commit();
               if (Cfg::NSTG == 1) bulk_wait_read<0>();
             }
@@ -648,8 +678,15 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     if (lane == 0) {
       tmap::prefetch_desc(&tmK);
       tmap::prefetch_desc(&tmV);
-      for (int it_seq = 0; it_seq < my_items; ++it_seq) {
-        const TmItem it = item_of(it_seq);
+    }
+    // Bulk L2 prefetch of the cell's query rows, one item ahead: the CTA of head 0 pulls the rows of ALL heads
+    // (whole pixels, one contiguous run per guidance row), so that DRAM sees one sequential read burst per cell
+    // instead of sector-sized reads scattered between the output writes; the per-tile register loads then hit L2.
+    const bool qbulk = NAF_TMA_QBULK && p.q_stride_x == p.D && !(NAF_TMA_EXP & 2);
+    const int qes = p.q_dtype == NAF_DTYPE_BF16 ? 2 : 4;
+    for (int it_seq = 0; it_seq < my_items; ++it_seq) {
+      const TmItem it = item_of(it_seq);
+      if (lane == 0) {
         const int wy0 = window_origin(it.ci, p.h, K), wx0 = window_origin(it.cj, p.w, K);
         const int kb = it_seq & 1;
         if (it_seq >= 2) mbar_wait(&bar_k_free[kb], ((it_seq >> 1) - 1) & 1);
@@ -666,6 +703,18 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         const int gk = (it.b * 2) * gm.groups_k + it.head * KC;
         tmap::load4(kdst, &tmK, 0, wx0, wy0, gk, &bar_k_full[kb]);
         tmap::load4(kdst + Cfg::kKStride, &tmK, 0, wx0, wy0, gk + gm.groups_k, &bar_k_full[kb]);
+      }
+      __syncwarp();
+      if (qbulk && it.head == 0) {
+        const int ey0 = tm_div(it.ci * rh, dv.rep_y), ey1 = tm_div(it.ci * rh + rh - 1, dv.rep_y);
+        const int ex0 = tm_div(it.cj * rw, dv.rep_x), ex1 = tm_div(it.cj * rw + rw - 1, dv.rep_x);
+        const uint32_t bytes = uint32_t(ex1 - ex0 + 1) * uint32_t(p.D) * qes;
+        const uint8_t* base = reinterpret_cast<const uint8_t*>(p.q) +
+                              (int64_t(it.b) * p.q_stride_b + int64_t(ex0) * p.q_stride_x) * qes;
+        for (int ey = ey0 + lane; ey <= ey1; ey += 32) bulk_prefetch_l2(base + int64_t(ey) * p.q_stride_y * qes, bytes);
+      }
+      if (lane == 0) {
+        const int wy0 = window_origin(it.ci, p.h, K), wx0 = window_origin(it.cj, p.w, K);
         const int vb = Cfg::NVB == 2 ? (it_seq & 1) : 0;
         const int vuse = Cfg::NVB == 2 ? (it_seq >> 1) : it_seq;     // how often this buffer has been filled before
         if (vuse >= 1) mbar_wait(&bar_v_free[vb], (vuse - 1) & 1);
@@ -675,8 +724,8 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         tmap::load4(vdst, &tmV, 0, wx0, wy0, gv, &bar_v_full[vb]);
         tmap::load4(vdst + Cfg::kVStride, &tmV, 0, wx0, wy0, gv + gm.groups_v, &bar_v_full[vb]);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ======================================================================== MMA ISSUER
     if (lane == 0) {
