@@ -30,6 +30,7 @@
 // Reference semantics: src/layers/attentions.py:16-29,53-75; RoPE src/layers/rope.py:137-153.
 #include <cuda_bf16.h>
 
+#include <cstring>
 #include <type_traits>
 
 #include "naf_common.cuh"
@@ -167,8 +168,10 @@ struct TmGeom {
   int th_last;         // rows of the last tile
   int n_items;
   int groups_k, groups_v;   // channel groups per (batch, plane) of the K / V plane tensors: D/8, C/8
-  int tab_bytes;            // RoPE table rows of one cell staged in shared memory per K window buffer
-                            // ([cos_y | sin_y] rh rows, [cos_x | sin_x] rw rows, 64 B each); 0 = read them from global
+  int tab_bytes;            // RoPE table rows of one cell staged in shared memory per K window buffer: [cos_y | sin_y]
+                            // rh rows of 64 B, then [cos_x | sin_x] as 4 chunk planes [chunk][column][16 B] of
+                            // xchunk bytes each (a lane reads its column's 16 bytes: conflict-free); 0 = tables from global
+  int xchunk;               // bytes of one chunk plane of an x table (rw * 16 rounded up to 128)
 };
 
 }  // namespace
@@ -218,7 +221,8 @@ template <int TP, int DVH, int NH, int ROUNDS, int NOB>
 __global__ void __launch_bounds__(NTHREADS, 1)
 xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
-                      const __grid_constant__ CUtensorMap tmO2) {
+                      const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmCX,
+                      const __grid_constant__ CUtensorMap tmSX) {
   using Cfg = TmaCfg<TP, DVH, NH, ROUNDS, NOB>;
   constexpr int K = Cfg::K, K2 = Cfg::K2;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -373,12 +377,14 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
           const int kb = (q_flags >> 2) & 1;
           if (q_flags & 1) mbar_wait(&bar_k_full[kb], (q_flags >> 3) & 1);
           const float* tb = sTab + kb * (gm.tab_bytes / 4);
-          const float* ct = half == 0 ? tb + q_r * P : tb + 2 * rh * P + q_c * P;
-          const float* st = ct + (half == 0 ? rh : rw) * P;
+          // row tables: one 64-byte row per pixel row (a broadcast read); column tables: chunk planes
+          const float* ct = half == 0 ? tb + q_r * P : tb + 2 * rh * P + q_c * 4;
+          const float* st = ct + (half == 0 ? rh * P : gm.xchunk);              // xchunk bytes * 4 chunks = floats
+          const int cs = half == 0 ? 4 : gm.xchunk / 4;                         // floats between 4-channel chunks
 #pragma unroll
           for (int j = 0; j < P; j += 4) {
-            *reinterpret_cast<float4*>(&c[j]) = *reinterpret_cast<const float4*>(ct + j);
-            *reinterpret_cast<float4*>(&sn[j]) = *reinterpret_cast<const float4*>(st + j);
+            *reinterpret_cast<float4*>(&c[j]) = *reinterpret_cast<const float4*>(ct + (j >> 2) * cs);
+            *reinterpret_cast<float4*>(&sn[j]) = *reinterpret_cast<const float4*>(st + (j >> 2) * cs);
           }
         } else {
           const float* ct = half == 0 ? p.cos_y + int64_t(q_r) * P : p.cos_x + int64_t(q_c) * P;
@@ -678,6 +684,10 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     if (lane == 0) {
       tmap::prefetch_desc(&tmK);
       tmap::prefetch_desc(&tmV);
+      if (gm.tab_bytes) {
+        tmap::prefetch_desc(&tmCX);
+        tmap::prefetch_desc(&tmSX);
+      }
     }
     // Bulk L2 prefetch of the cell's query rows, one item ahead: the CTA of head 0 pulls the rows of ALL heads
     // (whole pixels, one contiguous run per guidance row), so that DRAM sees one sequential read burst per cell
@@ -690,14 +700,19 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         const int wy0 = window_origin(it.ci, p.h, K), wx0 = window_origin(it.cj, p.w, K);
         const int kb = it_seq & 1;
         if (it_seq >= 2) mbar_wait(&bar_k_free[kb], ((it_seq >> 1) - 1) & 1);
-        mbar_expect_tx(&bar_k_full[kb], 2 * Cfg::kKPlane + gm.tab_bytes);
+        mbar_expect_tx(&bar_k_full[kb], 2 * Cfg::kKPlane + (gm.tab_bytes ? 2 * (rh + rw) * (DQ / 4) * 4 : 0));
         if (gm.tab_bytes) {
           float* tb = const_cast<float*>(sTab) + kb * (gm.tab_bytes / 4);
           constexpr int P = DQ / 4;
           bulk_load(tb, p.cos_y + int64_t(it.ci) * rh * P, rh * P * 4, &bar_k_full[kb]);
           bulk_load(tb + rh * P, p.sin_y + int64_t(it.ci) * rh * P, rh * P * 4, &bar_k_full[kb]);
-          bulk_load(tb + 2 * rh * P, p.cos_x + int64_t(it.cj) * rw * P, rw * P * 4, &bar_k_full[kb]);
-          bulk_load(tb + (2 * rh + rw) * P, p.sin_x + int64_t(it.cj) * rw * P, rw * P * 4, &bar_k_full[kb]);
+          float* tx = tb + 2 * rh * P;
+          const int xc = gm.xchunk / 4;   // floats per chunk plane
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            tmap::load4(tx + c * xc, &tmCX, 4 * c, it.cj * rw, 0, 0, &bar_k_full[kb]);
+            tmap::load4(tx + (4 + c) * xc, &tmSX, 4 * c, it.cj * rw, 0, 0, &bar_k_full[kb]);
+          }
         }
         uint8_t* kdst = sK + kb * Cfg::kKWin;
         const int gk = (it.b * 2) * gm.groups_k + it.head * KC;
@@ -864,7 +879,8 @@ int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
     gm.groups_k = p.D / 8;
     gm.groups_v = p.C / 8;
     // RoPE table rows of a cell in shared memory (one set per K window buffer) when there is room for them
-    gm.tab_bytes = p.cos_y ? 2 * (gm.rh + gm.rw) * (DQ / 4) * 4 : 0;
+    gm.xchunk = (gm.rw * 16 + 127) / 128 * 128;
+    gm.tab_bytes = p.cos_y ? 2 * gm.rh * (DQ / 4) * 4 + 8 * gm.xchunk : 0;
     if (Cfg::kSmemBytes + Cfg::NKB * gm.tab_bytes > kSmemLimit) gm.tab_bytes = 0;
     const int smem_bytes = Cfg::kSmemBytes + Cfg::NKB * gm.tab_bytes;
     const cudaError_t e = ensure_dyn_smem(kern, smem_bytes);
@@ -903,7 +919,18 @@ int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
       if (rc != NAF_OK) return rc;
     }
     // ---- tensor maps
-    CUtensorMap tmK, tmV, tmO, tmO2;
+    CUtensorMap tmK, tmV, tmO, tmO2, tmCX, tmSX;
+    memset(&tmCX, 0, sizeof(tmCX));
+    memset(&tmSX, 0, sizeof(tmSX));
+    if (gm.tab_bytes) {
+      // column tables (Wo, 16) fp32: box = 4 channels x rw columns, one load per chunk plane
+      const uint64_t dt_[4] = {16, uint64_t(p.Wo), 1, 1};
+      const uint64_t st_[3] = {64, uint64_t(p.Wo) * 64, uint64_t(p.Wo) * 64};
+      const uint32_t bt_[4] = {4, uint32_t(gm.rw), 1, 1};
+      if (!tmap::encode4(&tmCX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.cos_x, dt_, st_, bt_, CU_TENSOR_MAP_SWIZZLE_NONE) ||
+          !tmap::encode4(&tmSX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, p.sin_x, dt_, st_, bt_, CU_TENSOR_MAP_SWIZZLE_NONE))
+        return fail(NAF_ERR_CUDA, "xattn(cell-tma): cuTensorMapEncodeTiled failed (rope tables)");
+    }
     {
       const uint64_t dk[4] = {8, uint64_t(p.w), uint64_t(p.h), uint64_t(p.B) * 2 * (p.D / 8)};
       const uint64_t dvv[4] = {8, uint64_t(p.w), uint64_t(p.h), uint64_t(p.B) * 2 * (p.C / 8)};
@@ -924,7 +951,7 @@ int launch_tma(const naf_xattn_params& p, cudaStream_t st) {
         return fail(NAF_ERR_CUDA, "xattn(cell-tma): cuTensorMapEncodeTiled failed");
     }
     const int grid = int(items < sms ? items : sms);
-    kern<<<grid, NTHREADS, smem_bytes, st>>>(p, gm, dv, tmK, tmV, tmO, tmO2);
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(p, gm, dv, tmK, tmV, tmO, tmO2, tmCX, tmSX);
     return check_launch("xattn_cell_tma");
   }
 }

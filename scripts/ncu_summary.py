@@ -19,7 +19,13 @@ keys = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__
         "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__inst_executed.sum", "sm__cycles_active.avg",
         "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        # tensor-memory traffic (captured with --metrics on top of --set full, see scripts/gpu_r3_final.sh)
+        "sm__mem_tensor_reads.sum", "sm__mem_tensor_writes.sum", "sm__mem_tensor_reads_op_utcmma_matrix_c.sum",
+        "sm__mem_tensor_writes_op_utcmma.sum", "sm__inst_executed_pipe_tmem.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_a.sum",
+        "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_b_scope_1cta.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__cycles_elapsed.avg"]
 for h, u, v in zip(hdr, units, vals):
     if h in keys or h.startswith("smsp__average_warps_issue_stalled") and "per_issue_active" in h and float(v or 0) > 0.15:
         print(f"{h:86s} {v:>16s} {u}")

@@ -12,6 +12,8 @@ if not os.path.isfile(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
 L = C.CDLL(lib)
 L.store_probe.restype = C.c_int
 L.store_probe.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p]
+L.store_probe_rw.restype = C.c_int
+L.store_probe_rw.argtypes = [C.c_void_p] + [C.c_int] * 11 + [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]
 dev = torch.device("cuda", 0)
 Ho = Wo = 28 * 7 * 16      # 3136: 112 x 16 cells
 Cn, DV, th, tw = 768, 192, 4, 28
@@ -57,4 +59,31 @@ print(f"torch fill_ of {out.numel() * 4 / 1e9:.2f} GB: {ms:.3f} ms  {out.numel()
 # whole pixels (all 768 channels contiguous, 3 KB per pixel): does the chunk size matter?
 run(2, 1, 1, tag="unswizzled box of 256 channels x 28 x 4 pixels (1 KB contiguous per pixel)", DV=256, th=4)
 run(1, 0, 1, tag="per-thread 1-D bulk copies 1536 B (all 768 channels, 2 threads per pixel)", DV=768, th=2)
-run(2, 1, 2, tag="unswizzled box 384 channels x 28 x 4", DV=384, th=4)
+
+
+# ---- the launch's read : write mix without any compute: tensor stores as in the kernel + a paced stream of
+# 32-byte query loads (8 KB per tile ~ C2 through rep=2: 7 KB; 28 KB per tile = C2 with x at the target resolution)
+rd = torch.randn(512 * 1024 * 1024, device=dev)   # 2 GB read buffer
+sink = torch.zeros(1, device=dev)
+def run_rw(rbytes, mode=0, per_group=3, slots=2, tag=""):
+    st = torch.cuda.current_stream().cuda_stream
+    args = (out.data_ptr(), Ho, Wo, Cn, mode, iters, th, tw, DV, per_group, slots, 148, st, rd.data_ptr(), rbytes, rd.numel(), sink.data_ptr())
+    for _ in range(2):
+        rc = L.store_probe_rw(*args)
+        assert rc == 0, rc
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 3
+    for _ in range(n):
+        L.store_probe_rw(*args)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    wgb = 148 * iters * 7 * th * tw * DV * 4 / 1e9
+    rgb = 148 * iters * 7 * rbytes / 1e9
+    print(f"stores + reads, {rbytes} B read per tile, mode {mode} {tag}: {ms:.3f} ms  written {wgb:.2f} GB + read {rgb:.2f} GB = {(wgb + rgb) / ms * 1e3:.0f} GB/s total")
+run_rw(0, tag="(no reads, 384-thread launch)")
+run_rw(8192, tag="(C2 mix, x through rep=2)")
+run_rw(28672, tag="(C2 mix, x at target resolution)")
+run_rw(8192, mode=2, per_group=1, tag="(unswizzled 192-channel boxes)")
+run_rw(28672, mode=2, per_group=1, tag="(unswizzled 192-channel boxes)")

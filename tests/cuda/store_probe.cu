@@ -13,15 +13,44 @@
 using namespace naf::umma;
 namespace tmx = naf::tmap;
 
-extern "C" __global__ void __launch_bounds__(256, 1)
+// Optional read stream (rd != nullptr): warps 8-11 read `rbytes` bytes per tile from a second buffer with the
+// attention kernel's query-load instruction (32-byte ld.global.nc.L1::no_allocate), at most two tiles ahead of
+// the store thread -- the read : write mix of the real launch without any compute.
+extern "C" __global__ void __launch_bounds__(384, 1)
 store_probe_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ out, int mode, int iters, int th, int tw,
-                   int DV, int per_group, int slots, int cells_x, int cells_y, int heads, int Wo, int Ho, int C) {
+                   int DV, int per_group, int slots, int cells_x, int cells_y, int heads, int Wo, int Ho, int C,
+                   const float* __restrict__ rd, int rbytes, long long rd_elems, float* __restrict__ sink) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ volatile int s_tile;   // tiles the store thread has issued
   const int tid = threadIdx.x;
+  if (tid == 0) s_tile = 0;
+  if (tid >= 256) {
+    __syncthreads();
+    if (rd != nullptr && rbytes > 0) {
+      const int rt = tid - 256;
+      const int per_thread = rbytes / 32 / 128;   // 32-byte loads per reader thread and tile
+      float acc = 0.f;
+      long long pos = (long long)blockIdx.x * (rbytes / 4);
+      for (int t = 0; t < iters * 7; ++t) {
+        while (t > s_tile + 2) __nanosleep(64);
+        for (int j = 0; j < per_thread; ++j) {
+          float v[8];
+          const float* src = rd + (pos + (long long)(j * 128 + rt) * 8) % rd_elems;
+          asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                       : "l"(src));
+          acc += v[0] + v[7];
+        }
+        pos += (long long)gridDim.x * (rbytes / 4);
+      }
+      if (acc == 123.456f) *sink = acc;
+    }
+    return;
+  }
   // something finite in the staging area
   for (int i = tid; i < 200 * 1024 / 4; i += 256) reinterpret_cast<float*>(smem)[i] = float(i & 1023);
   fence_proxy_async_smem();
-  __syncthreads();
+  __syncthreads();   // (the reader warps take part in this one barrier only)
   const int ncell = cells_x * cells_y * heads;
   int cell = blockIdx.x;
   if (mode == 0 || mode == 2) {
@@ -46,6 +75,7 @@ store_probe_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
                           smem + size_t(slot) * per_group * box_bytes + size_t(j) * box_bytes);
             bulk_commit();
           }
+          s_tile = it * tiles + t + 1;
         }
       }
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -66,6 +96,7 @@ store_probe_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
           bulk_store(out + (int64_t(y) * Wo + x) * C + head * DV + half * (DV / 2), my, bytes);
         }
         bulk_commit();
+        if (tid == 0) s_tile = it * tiles + t + 1;
       }
     }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -73,8 +104,18 @@ store_probe_kernel(const __grid_constant__ CUtensorMap map, float* __restrict__ 
 }
 
 extern "C" __attribute__((visibility("default")))
+int store_probe_rw(float* out, int Ho, int Wo, int C, int mode, int iters, int th, int tw, int DV, int per_group, int slots,
+                   int grid, void* stream, const float* rd, int rbytes, long long rd_elems, float* sink);
+
+extern "C" __attribute__((visibility("default")))
 int store_probe(float* out, int Ho, int Wo, int C, int mode, int iters, int th, int tw, int DV, int per_group, int slots,
                 int grid, void* stream) {
+  return store_probe_rw(out, Ho, Wo, C, mode, iters, th, tw, DV, per_group, slots, grid, stream, nullptr, 0, 1, nullptr);
+}
+
+extern "C" __attribute__((visibility("default")))
+int store_probe_rw(float* out, int Ho, int Wo, int C, int mode, int iters, int th, int tw, int DV, int per_group, int slots,
+                   int grid, void* stream, const float* rd, int rbytes, long long rd_elems, float* sink) {
   CUtensorMap map;
   const uint64_t dims[4] = {uint64_t(C), uint64_t(Wo), uint64_t(Ho), 1};
   const uint64_t strides[3] = {uint64_t(C) * 4, uint64_t(Wo) * C * 4, uint64_t(Ho) * Wo * C * 4};
@@ -86,7 +127,8 @@ int store_probe(float* out, int Ho, int Wo, int C, int mode, int iters, int th, 
   const int smem = 200 * 1024;
   cudaFuncSetAttribute(store_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int cells_x = Wo / tw, cells_y = Ho / (th * 7), heads = C / DV;
-  store_probe_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(map, out, mode, iters, th, tw, DV, per_group,
-                                                                           slots, cells_x, cells_y, heads, Wo, Ho, C);
+  store_probe_kernel<<<grid, 384, smem, static_cast<cudaStream_t>(stream)>>>(map, out, mode, iters, th, tw, DV, per_group,
+                                                                           slots, cells_x, cells_y, heads, Wo, Ho, C, rd,
+                                                                           rbytes, rd_elems, sink);
   return int(cudaGetLastError());
 }
