@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define NAF_ABI_VERSION 3
+#define NAF_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define NAF_API __attribute__((visibility("default")))
@@ -117,7 +117,7 @@ NAF_API int naf_rope_kpool_f32(const naf_kpool_params* p, void* stream);
  *   s[t,u] = scale * <q[b,y,x,head], k[b,row_tap[y][t],col_tap[x][u],head]>
  *   p      = softmax_{t,u}(s)
  *   out[b,y,x,head] = sum_{t,u} p[t,u] * v[b,row_tap[y][t],col_tap[x][u],head]
- * row_tap (Ho,K) / col_tap (Wo,K) are int32 DEVICE tables holding the composition of NATTEN's
+ * row_tap (Ho,K) / col_tap (Wo,K) [(Wo,Kw) for a rectangular window, see Kw] are int32 DEVICE tables holding the composition of NATTEN's
  * shifted dilated window with F.interpolate(mode="nearest-exact").  They may
  * both be NULL iff Ho % h == 0 and Wo % w == 0: then the window of a pixel is the clamped
  * low-resolution window  clamp(y/(Ho/h) - K/2, 0, h-K) + t  shared by its whole cell.
@@ -154,7 +154,10 @@ typedef struct naf_xattn_params {
                             strides in elements).  bf16 is what the reference feeds under torch.autocast(bfloat16)
                             (train.py:120); it is read as it is by the TMA kernel (NAF_ALGO_CELL_TMA) -- the other
                             kernels take fp32 only and refuse (callers widen for them). */
-  int32_t reserved_;
+  int32_t Kw;            /* window WIDTH (taps along x) of a rectangular window, NATTEN's kernel_size=(K, Kw)
+                            (src/layers/attentions.py:20,24 pass the tuple through); 0 = square, Kw = K.  K is then the
+                            window HEIGHT, row_tap is (Ho,K), col_tap (Wo,Kw), the scores (…,K*Kw) in tap order
+                            t_h*Kw + t_w.  Rectangular windows run on the generic kernel (AUTO picks it). */
 } naf_xattn_params;
 
 enum { NAF_DTYPE_F32 = 0, NAF_DTYPE_BF16 = 1, NAF_DTYPE_F16 = 2 /* encoder activations only */ };
@@ -206,6 +209,8 @@ typedef struct naf_xattn_bwd_params {
   int64_t q_stride_b, q_stride_y, q_stride_x; /* elements */
   int32_t algo;
   int32_t rep_y, rep_x;
+  int32_t Kw;            /* window width of a rectangular window (0 = square), as in naf_xattn_params (ABI v4) */
+  int32_t reserved_;
 } naf_xattn_bwd_params;
 
 NAF_API int naf_xattn_bwd_f32(const naf_xattn_bwd_params* p, void* stream);

@@ -12,7 +12,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NAF_B200_LIB") or os.path.join(_HERE, "csrc", "libnaf_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 NAF_OK, NAF_ERR_BAD_SHAPE, NAF_ERR_UNSUPPORTED, NAF_ERR_WINDOW, NAF_ERR_ALIGNMENT, NAF_ERR_NULL, NAF_ERR_CUDA = range(7)
 ALGO_AUTO, ALGO_GENERIC, ALGO_CELL_SIMT, ALGO_CELL_TC, ALGO_CELL_TCWS, ALGO_CELL_TMA, ALGO_UNION_TC = range(7)
@@ -53,7 +53,7 @@ class XAttnParams(C.Structure):
         ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
         ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32), ("out_dtype", C.c_int32),
         ("workspace", _fp), ("workspace_bytes", C.c_int64),
-        ("q_dtype", C.c_int32), ("k_dtype", C.c_int32), ("v_dtype", C.c_int32), ("reserved_", C.c_int32),
+        ("q_dtype", C.c_int32), ("k_dtype", C.c_int32), ("v_dtype", C.c_int32), ("Kw", C.c_int32),
     ]
 
     def __init__(self, *a, **kw):
@@ -73,6 +73,7 @@ class XAttnBwdParams(C.Structure):
         ("scale", C.c_float),
         ("q_stride_b", C.c_int64), ("q_stride_y", C.c_int64), ("q_stride_x", C.c_int64),
         ("algo", C.c_int32), ("rep_y", C.c_int32), ("rep_x", C.c_int32),
+        ("Kw", C.c_int32), ("reserved_", C.c_int32),
     ]
 
     def __init__(self, *a, **kw):

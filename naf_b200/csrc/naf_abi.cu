@@ -95,6 +95,9 @@ static int validate_xattn(const naf_xattn_params& p) {
               "value channels (%d) must be divisible by num_heads (%d)", p.C, p.heads);
   NAF_REQUIRE(p.K >= 1 && (p.K & 1), NAF_ERR_WINDOW, "kernel_size must be odd and >= 1, got %d",
               p.K);
+  NAF_REQUIRE(p.Kw == 0 || (p.Kw >= 1 && (p.Kw & 1)), NAF_ERR_WINDOW,
+              "kernel_size must be odd and >= 1, got (%d, %d)", p.K, p.Kw);
+  const int kw_ = p.Kw ? p.Kw : p.K;
   const bool have_tables = p.row_tap && p.col_tap;
   NAF_REQUIRE(have_tables || (!p.row_tap && !p.col_tap), NAF_ERR_NULL,
               "xattn: row_tap and col_tap must both be given or both be NULL");
@@ -105,10 +108,10 @@ static int validate_xattn(const naf_xattn_params& p) {
   }
   // NATTEN's constraint kernel_size * dilation <= axis length (dilation = Ho // h)
   NAF_REQUIRE(p.Ho / p.h >= 1 && p.Wo / p.w >= 1 && int64_t(p.K) * (p.Ho / p.h) <= p.Ho &&
-                  int64_t(p.K) * (p.Wo / p.w) <= p.Wo,
+                  int64_t(kw_) * (p.Wo / p.w) <= p.Wo,
               NAF_ERR_WINDOW,
-              "kernel_size*dilation exceeds the target size (K=%d, target %dx%d, features %dx%d)",
-              p.K, p.Ho, p.Wo, p.h, p.w);
+              "kernel_size*dilation exceeds the target size (K=%dx%d, target %dx%d, features %dx%d)",
+              p.K, kw_, p.Ho, p.Wo, p.h, p.w);
   const int nrope = (p.cos_y != nullptr) + (p.sin_y != nullptr) + (p.cos_x != nullptr) +
                     (p.sin_x != nullptr);
   NAF_REQUIRE(nrope == 0 || nrope == 4, NAF_ERR_NULL,
@@ -137,6 +140,11 @@ static int select_algo(const naf_xattn_params& p, bool explain) {
                                        "tensors to the other kernels", why);
   }
   if (p.algo == NAF_ALGO_GENERIC) return NAF_ALGO_GENERIC;
+  if (p.Kw != 0 && p.Kw != p.K) {
+    // rectangular windows (NATTEN kernel_size=(kh, kw)): the generic kernel
+    if (p.algo == NAF_ALGO_AUTO) return NAF_ALGO_GENERIC;
+    return -fail(NAF_ERR_UNSUPPORTED, "xattn: rectangular windows (%dx%d) run on the generic kernel only", p.K, p.Kw);
+  }
   if (p.algo == NAF_ALGO_CELL_TMA) {
     if (xattn_cell_tma_supported(p, &why)) return NAF_ALGO_CELL_TMA;
     return -fail(NAF_ERR_UNSUPPORTED, "xattn: TMA tensor-core cell kernel unsupported: %s", why);
@@ -257,6 +265,7 @@ int naf_xattn_bwd_f32(const naf_xattn_bwd_params* pp, void* stream) {
   f.row_tap = p.row_tap; f.col_tap = p.col_tap;
   f.cos_y = p.cos_y; f.sin_y = p.sin_y; f.cos_x = p.cos_x; f.sin_x = p.sin_x;
   f.B = p.B; f.D = p.D; f.C = p.C; f.heads = p.heads; f.Ho = p.Ho; f.Wo = p.Wo; f.h = p.h; f.w = p.w; f.K = p.K;
+  f.Kw = p.Kw;
   f.scale = p.scale;
   f.q_stride_b = p.q_stride_b; f.q_stride_y = p.q_stride_y; f.q_stride_x = p.q_stride_x;
   f.rep_y = p.rep_y; f.rep_x = p.rep_x;

@@ -40,7 +40,8 @@ __device__ __forceinline__ void red_add(float* p, float v) {
 __global__ void __launch_bounds__(kBwdWarps * 32)
 xattn_bwd_generic_kernel(naf_xattn_bwd_params p, int rh, int rw, int64_t total_items) {
   extern __shared__ float smem_f[];
-  const int K2 = p.K * p.K;
+  const int Kh = p.K, Kw = p.Kw ? p.Kw : p.K;
+  const int K2 = Kh * Kw;
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_warp = 3 * K2 + dq + dv;
@@ -81,9 +82,9 @@ xattn_bwd_generic_kernel(naf_xattn_bwd_params p, int rh, int rw, int64_t total_i
     const float* gp = p.dout + pixoff * p.C + head * dv;
     for (int c = lane; c < dv; c += 32) sg[c] = gp[c];
     for (int tap = lane; tap < K2; tap += 32) {
-      const int t = tap / p.K, u = tap - t * p.K;
-      const int r = tap_index(p.row_tap, y, t, p.K, rh, p.h);
-      const int c = tap_index(p.col_tap, x, u, p.K, rw, p.w);
+      const int t = tap / Kw, u = tap - t * Kw;
+      const int r = tap_index(p.row_tap, y, t, Kh, rh, p.h);
+      const int c = tap_index(p.col_tap, x, u, Kw, rw, p.w);
       idx[tap] = (b * p.h + r) * p.w + c;
     }
     __syncwarp();
@@ -451,8 +452,11 @@ int launch_xattn_bwd(const naf_xattn_bwd_params& p, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(p.dk, 0, sizeof(float) * size_t(p.B) * p.h * p.w * p.D, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(p.dv, 0, sizeof(float) * size_t(p.B) * p.h * p.w * p.C, st);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn_bwd: memset failed: %s", cudaGetErrorString(e));
-  const int dq = p.D / p.heads, dv = p.C / p.heads, K2 = p.K * p.K;
-  {
+  const int dq = p.D / p.heads, dv = p.C / p.heads, K2 = p.K * (p.Kw ? p.Kw : p.K);
+  const bool rect = p.Kw != 0 && p.Kw != p.K;   // rectangular windows: the generic kernel
+  if (rect && p.algo != NAF_ALGO_AUTO && p.algo != NAF_ALGO_GENERIC)
+    return fail(NAF_ERR_UNSUPPORTED, "xattn_bwd: rectangular windows (%dx%d) run on the generic kernel only", p.K, p.Kw);
+  if (!rect) {
     // integer ratios, 64-wide heads, cells of >= 64 pixels: the five GEMMs on the tensor core (naf_xattn_bwd_tc.cu)
     const char* why = "";
     const bool tc_ok = xattn_bwd_cell_tc_supported(p, &why);
@@ -460,7 +464,7 @@ int launch_xattn_bwd(const naf_xattn_bwd_params& p, cudaStream_t st) {
     if (p.algo == NAF_ALGO_CELL_TC)
       return fail(NAF_ERR_UNSUPPORTED, "xattn_bwd: the tensor-core cell kernel does not support this request: %s", why);
   }
-  const int cell_nt = p.algo != NAF_ALGO_GENERIC ? bwd_cell_config(p) : 0;
+  const int cell_nt = (p.algo != NAF_ALGO_GENERIC && !rect) ? bwd_cell_config(p) : 0;
   if (cell_nt) return dq == 64 ? launch_bwd_cell<64>(p, cell_nt, st) : launch_bwd_cell<32>(p, cell_nt, st);
   if (p.algo == NAF_ALGO_CELL_SIMT)
     return fail(NAF_ERR_UNSUPPORTED, "xattn_bwd: the cell kernel does not support this request");

@@ -4,7 +4,7 @@
 // low-res maps are a few MB and stay cache resident).  The cell kernels are the fast paths.
 //
 // Reference semantics: src/layers/attentions.py:16-29 (QK -> *scale -> softmax -> AV),
-// :53-75 (dilation, layouts); tap order t_h*K + t_w (NATTEN).
+// :53-75 (dilation, layouts); tap order t_h*Kw + t_w (NATTEN); rectangular windows kernel_size=(Kh, Kw).
 #include <cuda_bf16.h>
 
 #include "naf_common.cuh"
@@ -16,7 +16,8 @@ constexpr int kGenericWarps = 4;
 __global__ void __launch_bounds__(kGenericWarps * 32)
 xattn_generic_kernel(naf_xattn_params p, int rh, int rw, int64_t total_items) {
   extern __shared__ float smem_f[];
-  const int K2 = p.K * p.K;
+  const int Kh = p.K, Kw = p.Kw ? p.Kw : p.K;   // window height / width (rectangular: NATTEN kernel_size=(Kh, Kw))
+  const int K2 = Kh * Kw;
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_warp = 2 * K2 + dq;
@@ -52,9 +53,9 @@ xattn_generic_kernel(naf_xattn_params p, int rh, int rw, int64_t total_items) {
       for (int i = lane; i < dq; i += 32) sq[i] = qp[i];
     }
     for (int tap = lane; tap < K2; tap += 32) {
-      const int t = tap / p.K, u = tap - t * p.K;
-      const int r = tap_index(p.row_tap, y, t, p.K, rh, p.h);
-      const int c = tap_index(p.col_tap, x, u, p.K, rw, p.w);
+      const int t = tap / Kw, u = tap - t * Kw;
+      const int r = tap_index(p.row_tap, y, t, Kh, rh, p.h);
+      const int c = tap_index(p.col_tap, x, u, Kw, rw, p.w);
       idx[tap] = (b * p.h + r) * p.w + c;
     }
     __syncwarp();
@@ -101,7 +102,7 @@ xattn_generic_kernel(naf_xattn_params p, int rh, int rw, int64_t total_items) {
 }
 
 int launch_xattn_generic(const naf_xattn_params& p, cudaStream_t st) {
-  const int K2 = p.K * p.K;
+  const int K2 = p.K * (p.Kw ? p.Kw : p.K);
   const int dq = p.D / p.heads;
   const size_t smem = size_t(kGenericWarps) * (2 * K2 + dq) * sizeof(float);
   NAF_REQUIRE(smem <= 200 * 1024, NAF_ERR_UNSUPPORTED,

@@ -232,6 +232,7 @@ static int cell_simt_warps(int K, int dq, int nj) {
 }
 
 bool xattn_cell_simt_supported(const naf_xattn_params& p, const char** why) {
+  if (p.Kw != 0 && p.Kw != p.K) { *why = "rectangular window"; return false; }
   if (p.out_dtype != NAF_DTYPE_F32) { *why = "fp32 output only"; return false; }
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }

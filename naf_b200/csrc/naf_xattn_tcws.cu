@@ -805,6 +805,7 @@ int launch_ws_tp(const naf_xattn_params& p, cudaStream_t st) {
 }  // namespace
 
 bool xattn_cell_tcws_supported(const naf_xattn_params& p, const char** why) {
+  if (p.Kw != 0 && p.Kw != p.K) { *why = "rectangular window"; return false; }
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }

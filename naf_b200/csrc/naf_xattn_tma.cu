@@ -1032,6 +1032,7 @@ int launch_tma_tp(const naf_xattn_params& p, cudaStream_t st) {
 size_t xattn_cell_tma_workspace(const naf_xattn_params& p) { return tm_workspace_bytes(p); }
 
 bool xattn_cell_tma_supported(const naf_xattn_params& p, const char** why) {
+  if (p.Kw != 0 && p.Kw != p.K) { *why = "rectangular window"; return false; }
   const int dq = p.D / p.heads, dv = p.C / p.heads;
   if (p.row_tap || p.col_tap) { *why = "tap tables given (non-integer ratio path)"; return false; }
   if (p.Ho % p.h || p.Wo % p.w) { *why = "target size is not a multiple of the feature size"; return false; }

@@ -438,6 +438,7 @@ bool fill_geom(const naf_xattn_params& p, UnionGeom& g, size_t& smem_bytes) {
 }  // namespace
 
 bool xattn_union_tc_supported(const naf_xattn_params& p, const char** why) {
+  if (p.Kw != 0 && p.Kw != p.K) { *why = "rectangular window"; return false; }
   if (p.q_dtype != NAF_DTYPE_F32 || p.k_dtype != NAF_DTYPE_F32 || p.v_dtype != NAF_DTYPE_F32) {
     *why = "fp32 inputs only";
     return false;

@@ -34,12 +34,15 @@ class CrossAttention(nn.Module):
         self.scale = (dim // num_heads) ** -0.5
         self.algo = _lib.ALGO_AUTO
 
-    def _square_kernel(self) -> int:
+    def _window(self):
+        """kernel_size as the kernels take it: an int for square windows, NATTEN's (kh, kw) pair otherwise
+        (rectangular windows run on the generic kernel)."""
         ks = self.kernel_size
         if isinstance(ks, (tuple, list)):
-            if len(ks) != 2 or int(ks[0]) != int(ks[1]):
-                raise NotImplementedError(f"naf_b200 supports square windows only, got {ks}")
-            return int(ks[0])
+            if len(ks) != 2:
+                raise ValueError(f"kernel_size must be an int or a pair, got {ks!r}")
+            kh, kw = int(ks[0]), int(ks[1])
+            return kh if kh == kw else (kh, kw)
         return int(ks)
 
     def forward(self, q, k, v, image=None, return_weights=False, rope_tables=None, rep=(1, 1), out_dtype=None,
@@ -52,9 +55,9 @@ class CrossAttention(nn.Module):
                 and tuple(rep) == (1, 1)):
             # differentiable like the reference's NATTEN calls (train.py:136): forward = the same kernels
             from ..autograd import XAttnFn
-            return XAttnFn.apply(q, k, v, self.num_heads, self._square_kernel(), self.scale, self.algo,
+            return XAttnFn.apply(q, k, v, self.num_heads, self._window(), self.scale, self.algo,
                                  out_dtype, bool(return_weights))
-        res = ops.xattn(q, k, v, self.num_heads, self._square_kernel(), scale=self.scale,
+        res = ops.xattn(q, k, v, self.num_heads, self._window(), scale=self.scale,
                         rope_tables=rope_tables, return_scores=return_weights, algo=self.algo, rep=rep,
                         out_dtype=out_dtype)
         return res

@@ -165,7 +165,7 @@ class NAF(nn.Module):
             if fused:
                 from ..autograd import NAFUpsampleFn
                 return NAFUpsampleFn.apply(x.float(), features, tables, pool_tables, rope.num_heads,
-                                           self.upsampler.num_heads, self.upsampler._square_kernel(),
+                                           self.upsampler.num_heads, self.upsampler._window(),
                                            self.upsampler.scale, self.upsampler.algo, (ry, rx), out_dtype)
             # rope heads != attention heads: compose the differentiable operators on the materialised map
             if (ry, rx) != (1, 1):

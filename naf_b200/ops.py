@@ -193,6 +193,7 @@ _tap_cache: dict = {}
 
 def device_tap_tables(Ho, Wo, h, w, K, dev):
     """int32 device tables (row_tap, col_tap) or (None, None) for integer ratios; cached."""
+    K = taps._pair(K)
     key = (Ho, Wo, h, w, K, str(dev))
     hit = _tap_cache.get(key)
     if hit is None:
@@ -217,7 +218,9 @@ def _fill_xattn(q, k, v, out, scores, heads, K, scale, tap_tabs, rope_tabs, algo
     p.row_tap, p.col_tap = _ptr(tap_tabs[0]), _ptr(tap_tabs[1])
     if rope_tabs is not None:
         p.cos_y, p.sin_y, p.cos_x, p.sin_x = (_ptr(t) for t in rope_tabs)
-    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
+    kh, kw = taps._pair(K)
+    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, kh
+    p.Kw = 0 if kw == kh else kw      # rectangular window (NATTEN kernel_size=(kh, kw)); 0 = square
     p.scale = float(scale)
     p.q_stride_b, _, p.q_stride_y, p.q_stride_x = q.stride()
     p.algo = int(algo)
@@ -246,13 +249,14 @@ def _launch_xattn(p, dev) -> None:
     _lib.check(rc, "naf_xattn_fwd_f32")
 
 
-def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_size: int,
+def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_size,
           scale: Optional[float] = None, rope_tables=None, return_scores: bool = False,
           algo: int = _lib.ALGO_AUTO, rep=(1, 1), out_dtype: torch.dtype = torch.float32):
     """Cross-scale neighbourhood attention.  q (B,D,Ho,Wo), k (B,D,h,w), v (B,C,h,w), all
     NCHW-shaped; returns out (B,C,Ho,Wo) as a permuted view of pixel-major storage (exactly what
     the reference returns, src/layers/attentions.py:75) and optionally the scaled pre-softmax
-    scores (B,heads,Ho,Wo,K*K).
+    scores (B,heads,Ho,Wo,K*K).  kernel_size: an odd int, or NATTEN's pair (kh, kw) -- rectangular windows
+    run on the generic kernel.
 
     out_dtype: torch.float32, or torch.bfloat16 (what the reference returns under bf16 autocast;
     the arithmetic stays fp32, only the final store is rounded).
@@ -270,14 +274,14 @@ def xattn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, kernel_
     Cn, h, w = v.shape[1:]
     if Cn % heads != 0:
         raise ValueError(f"value channels ({Cn}) must be divisible by num_heads ({heads})")
-    K = int(kernel_size)
+    K = taps._pair(kernel_size)
     if scale is None:
         scale = (D // heads) ** -0.5
     tap_tabs = device_tap_tables(Ho, Wo, h, w, K, dev)  # validates the window too
     if out_dtype not in (torch.float32, torch.bfloat16):
         raise NotImplementedError(f"xattn: out_dtype {out_dtype} (float32 or bfloat16)")
     out = torch.empty((B, Ho, Wo, Cn), device=dev, dtype=out_dtype)
-    scores = (torch.empty((B, heads, Ho, Wo, K * K), device=dev, dtype=torch.float32)
+    scores = (torch.empty((B, heads, Ho, Wo, K[0] * K[1]), device=dev, dtype=torch.float32)
               if return_scores else None)
     p = None
     if any(t.dtype == torch.bfloat16 for t in (q, k, v)) and algo in (_lib.ALGO_AUTO, _lib.ALGO_CELL_TMA):
@@ -317,7 +321,7 @@ def _contig_pixel_major(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
-def xattn_bwd(q, k, v, dout, heads: int, kernel_size: int, scale: Optional[float] = None, rope_tables=None,
+def xattn_bwd(q, k, v, dout, heads: int, kernel_size, scale: Optional[float] = None, rope_tables=None,
               algo: int = _lib.ALGO_AUTO, rep=(1, 1)):
     """Gradients of `xattn` (naf_xattn_bwd_f32).  q, k, v, rope_tables, rep, scale as given to the
     forward; dout (B,C,Ho,Wo) is dL/dout.  Returns (dq, dk, dv) as NCHW-shaped pixel-major views:
@@ -327,7 +331,7 @@ def xattn_bwd(q, k, v, dout, heads: int, kernel_size: int, scale: Optional[float
     B, D, Ho, Wo = q.shape
     Ho, Wo = Ho * int(rep[0]), Wo * int(rep[1])
     _, Cn, h, w = v.shape
-    K = int(kernel_size)
+    K = taps._pair(kernel_size)
     if tuple(dout.shape) != (B, Cn, Ho, Wo):
         raise ValueError(f"dout{tuple(dout.shape)} does not match the output shape {(B, Cn, Ho, Wo)}")
     if scale is None:
@@ -345,7 +349,8 @@ def xattn_bwd(q, k, v, dout, heads: int, kernel_size: int, scale: Optional[float
     p.row_tap, p.col_tap = _ptr(tap_tabs[0]), _ptr(tap_tabs[1])
     if rope_tables is not None:
         p.cos_y, p.sin_y, p.cos_x, p.sin_x = (_ptr(t) for t in rope_tables)
-    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
+    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K[0]
+    p.Kw = 0 if K[1] == K[0] else K[1]
     p.scale = float(scale)
     p.q_stride_b, _, p.q_stride_y, p.q_stride_x = q.stride()
     p.algo = int(algo)
@@ -387,12 +392,12 @@ def rope_kpool_bwd(dq, dk, tables, rope_heads: int, inplace: bool = False):
     return dx.permute(0, 3, 1, 2)
 
 
-def select_algo(q_shape, v_shape, heads: int, kernel_size: int, rope_on_the_fly: bool = True,
+def select_algo(q_shape, v_shape, heads: int, kernel_size, rope_on_the_fly: bool = True,
                 return_scores: bool = False) -> str:
     """Name of the kernel AUTO would pick for these shapes (no launch; dummy aligned pointers)."""
     B, D, Ho, Wo = q_shape
     _, Cn, h, w = v_shape
-    K = int(kernel_size)
+    K = taps._pair(kernel_size)
     rt, _ = taps.tap_tables(Ho, Wo, h, w, K)
     p = _lib.XAttnParams()
     dummy = 1 << 20
@@ -403,7 +408,8 @@ def select_algo(q_shape, v_shape, heads: int, kernel_size: int, rope_on_the_fly:
         p.row_tap = p.col_tap = dummy
     if rope_on_the_fly:
         p.cos_y = p.sin_y = p.cos_x = p.sin_x = dummy
-    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K
+    p.B, p.D, p.C, p.heads, p.Ho, p.Wo, p.h, p.w, p.K = B, D, Cn, heads, Ho, Wo, h, w, K[0]
+    p.Kw = 0 if K[1] == K[0] else K[1]
     p.scale = (D // heads) ** -0.5
     p.q_stride_b, p.q_stride_y, p.q_stride_x = Ho * Wo * D, Wo * D, D
     p.workspace, p.workspace_bytes = dummy, 1 << 62     # as ops.xattn provides it

@@ -87,3 +87,15 @@ def bwd_module_case(name):
                 dout=seeded_normal(seed + 2, (1, int(feats_shape[1]), Ho, Wo)), out=torch.from_numpy(d["out"]),
                 dimage=torch.from_numpy(d["dimage"]), dfeatures=torch.from_numpy(d["dfeatures"]),
                 output_size=(Ho, Wo), grads=grads)
+
+
+# ---- rectangular windows (oracle/gen_golden_rect.py: forward, scores and gradients from the unmodified reference)
+def rect_attention_case(name):
+    d = load(name)
+    seed = int(d["seed"])
+    q_shape, v_shape = d["q_shape"], d["v_shape"]
+    return dict(q=seeded_normal(seed, q_shape) * float(d["gain"]), k=seeded_normal(seed + 1, d["k_shape"]),
+                v=seeded_normal(seed + 2, v_shape), dout=seeded_normal(seed + 3, (q_shape[0], v_shape[1], q_shape[2], q_shape[3])),
+                out=torch.from_numpy(d["out"]), scores=torch.from_numpy(d["scores"]), dq=torch.from_numpy(d["dq"]),
+                dk=torch.from_numpy(d["dk"]), dv=torch.from_numpy(d["dv"]), heads=int(d["heads"]),
+                K=tuple(int(x) for x in d["kernel_size"]), dilation=tuple(int(x) for x in d["dilation"]))

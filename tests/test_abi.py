@@ -45,15 +45,18 @@ def test_struct_layouts_match_the_header():
 int main(void){
   printf("%zu %zu %zu %zu\n", sizeof(naf_kpool_params), offsetof(naf_kpool_params, B), offsetof(naf_kpool_params, x_stride_b), offsetof(naf_kpool_params, x_stride_x));
   printf("%zu %zu %zu %zu %zu\n", sizeof(naf_xattn_params), offsetof(naf_xattn_params, B), offsetof(naf_xattn_params, scale), offsetof(naf_xattn_params, q_stride_b), offsetof(naf_xattn_params, algo));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(naf_xattn_params, workspace), offsetof(naf_xattn_params, q_dtype), offsetof(naf_xattn_params, Kw), sizeof(naf_xattn_bwd_params), offsetof(naf_xattn_bwd_params, Kw));
   return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         cfile, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
         open(cfile, "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), cfile, "-o", exe])
-        l1, l2 = subprocess.check_output([exe], text=True).strip().splitlines()
+        l1, l2, l3 = subprocess.check_output([exe], text=True).strip().splitlines()
     kp, xp = _lib.KPoolParams, _lib.XAttnParams
     assert [int(v) for v in l1.split()] == [C.sizeof(kp), kp.B.offset, kp.x_stride_b.offset, kp.x_stride_x.offset]
     assert [int(v) for v in l2.split()] == [C.sizeof(xp), xp.B.offset, xp.scale.offset, xp.q_stride_b.offset, xp.algo.offset]
+    bp = _lib.XAttnBwdParams
+    assert [int(v) for v in l3.split()] == [xp.workspace.offset, xp.q_dtype.offset, xp.Kw.offset, C.sizeof(bp), bp.Kw.offset]
 
 
 def test_kernel_selection_for_baseline_configs():
@@ -68,6 +71,8 @@ def test_kernel_selection_for_baseline_configs():
     assert sel((8, 256, 256, 256), (8, 3, 256, 256), 1, 15) == "union_tc"  # denoising: ratio 1, C = 3, one head
     assert sel((1, 64, 32, 32), (1, 16, 13, 13), 4, 9, return_scores=True) == "generic"   # per-tap scores
     assert sel((1, 96, 32, 32), (1, 16, 13, 13), 4, 9) == "generic"     # head dim 24: not a multiple of 16
+    assert sel((8, 256, 896, 896), (8, 768, 32, 32), 4, (7, 5)) == "generic"   # rectangular window (NATTEN (kh, kw))
+    assert sel((8, 256, 896, 896), (8, 768, 32, 32), 4, (7, 7)) == "cell_tma"  # a pair with kh == kw is a square window
     assert sel((1, 256, 36, 36), (1, 32, 9, 9), 4, 7, return_scores=True) == "generic"      # 16-pixel cells
     assert sel((1, 256, 224, 224), (1, 384, 16, 16), 4, 7, return_scores=True) == "cell_tma"  # scores on the fast kernel
 

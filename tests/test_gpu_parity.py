@@ -117,6 +117,58 @@ def test_naf_module_matches_reference_golden(name):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+# ------------------------------------------------------------------ rectangular windows
+@pytest.mark.parametrize("name", G.names("rect_xattn_"))
+def test_rectangular_windows_match_reference_golden(name):
+    """kernel_size=(kh, kw) with kh != kw, as NATTEN takes it from the reference (src/layers/attentions.py:20,24):
+    forward, scores (tap order t_h*kw + t_w) and gradients against fixtures from the unmodified reference.  AUTO
+    routes these to the generic kernels (fp32: 2e-5); asking a cell kernel for one fails loudly."""
+    c = G.rect_attention_case(name)
+    D = c["q"].shape[1]
+    mod = naf_b200.CrossAttention(dim=D, num_heads=c["heads"], kernel_size=c["K"])
+    q, k, v, dout = (c[n].to(dev()) for n in ("q", "k", "v", "dout"))
+    assert ops.select_algo(q.shape, v.shape, c["heads"], c["K"], rope_on_the_fly=False) == "generic"
+    with torch.no_grad():
+        out = mod(q, k, v, None)
+        assert mod.dilation == c["dilation"]
+        assert (out.cpu() - c["out"]).abs().max().item() <= 2e-5
+        out, scores = mod(q, k, v, None, return_weights=True)
+        assert scores.shape == c["scores"].shape
+        assert (scores.cpu() - c["scores"]).abs().max().item() <= 2e-5
+        assert (out.cpu() - c["out"]).abs().max().item() <= 2e-5
+        for algo in (_lib.ALGO_CELL_SIMT, _lib.ALGO_CELL_TCWS, _lib.ALGO_CELL_TMA, _lib.ALGO_UNION_TC):
+            with pytest.raises(NotImplementedError):
+                ops.xattn(q, k, v, c["heads"], c["K"], algo=algo)
+    # gradients: the operator-level entry point and autograd through the module
+    dq, dk, dv = ops.xattn_bwd(q, k, v, dout, c["heads"], c["K"])
+    qg, kg, vg = (t.clone().requires_grad_(True) for t in (q, k, v))
+    mod(qg, kg, vg, None).backward(dout)
+    for got, got2, want, what in ((dq, qg.grad, c["dq"], "dq"), (dk, kg.grad, c["dk"], "dk"), (dv, vg.grad, c["dv"], "dv")):
+        scale = max(want.abs().max().item(), 1e-6)
+        assert (got.cpu() - want).abs().max().item() <= 3e-5 * scale, (name, what)
+        assert (got2.cpu() - want).abs().max().item() <= 3e-5 * scale, (name, what, "autograd")
+    with pytest.raises(NotImplementedError):
+        ops.xattn_bwd(q, k, v, dout, c["heads"], c["K"], algo=_lib.ALGO_CELL_SIMT)
+
+
+def test_rectangular_window_with_rope_and_replication_matches_oracle():
+    """The fused form NAF.forward uses (un-rotated guidance + rope tables, replicated source map) with a 5 x 9 window."""
+    torch.manual_seed(3)
+    B, D, C, heads, h, w, r, K = 1, 256, 32, 4, 9, 10, 4, (5, 9)
+    Ho, Wo = h * r, w * r
+    m = naf_b200.NAF(kernel_size=7).eval().to(dev())
+    m.upsampler.kernel_size = K
+    xs = torch.randn(B, D, Ho // 2, Wo // 2)
+    feats = torch.randn(B, C, h, w)
+    x_full = xs.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    want = O.naf_forward(x_full, feats, heads, 4, K)
+    tables = m.image_encoder.rope.axis_tables(Ho, Wo)
+    with torch.no_grad():
+        kk, _ = ops.rope_kpool(xs.to(dev()), tables, 4, pooled_hw=(h, w), rep=(2, 2))
+        out = m.upsampler(xs.to(dev()), kk, feats.to(dev()), rope_tables=tables, rep=(2, 2))
+    assert (out.cpu() - want).abs().max().item() <= 2e-5
+
+
 # ------------------------------------------------------------------ bit-exact neighbourhood indices
 @pytest.mark.parametrize("shape", [(36, 36, 9, 9, 7), (224, 224, 16, 16, 7), (1036, 1036, 37, 37, 11),
                                    (24, 40, 8, 10, 5), (32, 32, 13, 13, 9), (30, 45, 7, 11, 3),
@@ -257,8 +309,11 @@ def test_errors_on_device():
         ops.xattn(q, k, torch.zeros(1, 6, 4, 4, device=dev()), 4, 3)  # C % heads
     with pytest.raises(RuntimeError, match="forward pass only"):
         ops.xattn(q.requires_grad_(), k, v, 4, 3)
-    with pytest.raises(NotImplementedError):
-        naf_b200.CrossAttention(64, 4, (3, 5))(q.detach(), k, v)
+    with pytest.raises(ValueError):
+        naf_b200.CrossAttention(64, 4, (3, 5))(q.detach(), k, v)      # rectangular: kw*dilation = 20 > 16
+    with pytest.raises(ValueError):
+        naf_b200.CrossAttention(64, 4, (3, 4))(q.detach(), k, v)      # even width
+    assert naf_b200.CrossAttention(64, 4, (1, 3))(q.detach(), k, v).shape == (1, 8, 16, 16)
 
 
 # ------------------------------------------------------------------ full-size property tests

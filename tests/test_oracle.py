@@ -207,3 +207,17 @@ def test_oracle_gradients_match_reference_golden(name):
     dq, dk, dv = O.cross_attention_grads(c["q"], c["k"], c["v"], c["dout"], c["heads"], c["K"])
     for got, want in ((dq, c["dq"]), (dk, c["dk"]), (dv, c["dv"])):
         assert (got.float() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("name", G.names("rect_xattn_"))
+def test_rectangular_windows_match_reference_golden(name):
+    """NATTEN's kernel_size=(kh, kw) (the reference passes its tuple through, src/layers/attentions.py:20,24): the
+    oracle's forward, scores (tap order t_h*kw + t_w) and fp64 gradients against fixtures from the unmodified reference."""
+    c = G.rect_attention_case(name)
+    out, scores = O.cross_attention(c["q"], c["k"], c["v"], c["heads"], c["K"], return_weights=True)
+    assert scores.shape[-1] == c["K"][0] * c["K"][1]
+    assert (out - c["out"]).abs().max().item() <= TOL
+    assert (scores - c["scores"]).abs().max().item() <= 1e-5
+    dq, dk, dv = O.cross_attention_grads(c["q"], c["k"], c["v"], c["dout"], c["heads"], c["K"])
+    for got, want in ((dq, c["dq"]), (dk, c["dk"]), (dv, c["dv"])):
+        assert (got.float() - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item())

@@ -81,3 +81,18 @@ def test_union_window_multiplicity_softmax_equals_tap_softmax(Ho, Wo, h, w, K):
                     got = (vu @ e) / e.sum()
                     assert (got - want[:, y, x]).abs().max().item() <= 2e-6, (y, x)
     assert worst_span <= 32      # the kernel's RMAX: tables built from NATTEN windows stay inside it
+
+
+@pytest.mark.parametrize("shape", [(32, 40, 8, 10, (7, 5)), (27, 45, 9, 9, (3, 9)), (30, 45, 7, 11, (5, 3)), (896, 896, 32, 32, (7, 11))])
+def test_rectangular_window_tables_bit_exact_vs_oracle(shape):
+    """kernel_size=(kh, kw): row table (Ho, kh), column table (Wo, kw), each the square rule of its own axis."""
+    Ho, Wo, h, w, K = shape
+    rt_o, ct_o = O.tap_tables(Ho, Wo, h, w, K)
+    assert rt_o.shape == (Ho, K[0]) and ct_o.shape == (Wo, K[1])
+    assert (taps.axis_taps(Ho, h, K[0]) == rt_o).all() and (taps.axis_taps(Wo, w, K[1]) == ct_o).all()
+    rt, ct = taps.tap_tables(Ho, Wo, h, w, K)
+    if Ho % h == 0 and Wo % w == 0:
+        assert rt is None and ct is None
+        assert (taps.closed_form_axis_taps(Ho, h, K[0]) == rt_o).all() and (taps.closed_form_axis_taps(Wo, w, K[1]) == ct_o).all()
+    else:
+        assert (rt == rt_o).all() and (ct == ct_o).all()
