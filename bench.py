@@ -27,6 +27,8 @@ Rank 0 prints ONE JSON line.  Keys beyond the base contract:
                (tensor-core cell kernel) and the tap-table / ratio-1 forward (union-window tensor-core kernel)
   cpu_baseline the UNMODIFIED reference modules (oracle/_ref, NATTEN replaced by oracle/natten_stub.py) on
                the host cores, bounded sample (N=1, rank 0 only)
+  gpu_eager_reference  the same unmodified modules + stand-in run through torch eager on the B200 itself, one
+               full-size image (a same-device proxy for "the reference on a GPU"; NOT NATTEN)
 """
 from __future__ import annotations
 
@@ -193,6 +195,41 @@ def time_cpu_reference(workload, steps, warmup):
     desc = (f"{workload} {size}: guidance {s['guide']}^2 -> target {s['target']}^2, features "
             f"{s['C']}x{s['low']}x{s['low']}, r={s['r']}, K={s['K']}, batch 1; {what}")
     return mpix / dt, dt * 1e3, desc, kind
+
+
+def time_gpu_eager_reference(workload, dev, steps=3, warmup=1):
+    """The same UNMODIFIED reference modules (oracle/_ref) + torch NATTEN stand-in, but on the B200 itself: cuDNN
+    convolutions, ATen elementwise / gather kernels, the replicated K and V and the (B,n,Ho,Wo,K*K) attention tensor
+    in HBM like the reference's NATTEN path keeps them.  NOT NATTEN (not installable offline): a same-device proxy for
+    "the reference on a GPU", one full-size image of the workload.  None when oracle/_ref is absent."""
+    from oracle import reference_runner as R
+
+    if not R.available():
+        return None
+    _, C, gi, to, lo, K = WORKLOADS[workload]
+    torch.manual_seed(0)
+    model = R.load().NAF(kernel_size=K).eval().to(dev)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    image = torch.randn(1, 3, gi, gi, generator=g).to(dev)
+    feats = torch.randn(1, C, lo, lo, generator=g).to(dev)
+    with torch.no_grad():
+        for _ in range(warmup):
+            out = model(image, feats, (to, to))
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = model(image, feats, (to, to))
+        e1.record()
+        torch.cuda.synchronize(dev)
+    del out
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": round(to * to / 1e6 / (ms / 1e3), 3), "unit": "Mpix/s", "ms_per_image": round(ms, 2),
+            "kind": "reference modules on the same GPU through torch eager (NOT NATTEN)",
+            "sample": f"{workload}, ONE image at full size (guidance {gi}^2 -> target {to}^2, features {C}x{lo}x{lo}, K={K}); "
+                      "unmodified src/model/naf.py NAF.forward from oracle/_ref, NATTEN's na2d_qk / na2d_av replaced by "
+                      "oracle/natten_stub.py (pure torch, 16 target rows per gather), cuDNN convolutions with PyTorch's "
+                      "default TF32"}
 
 
 def run_reference_arm(args, rank):
@@ -643,6 +680,13 @@ def main():
             v1, ms1, d1, k1 = time_cpu_reference("C1", steps=2, warmup=1)
             line["cpu_baseline"]["C1_full_size"] = {"value": round(v1, 5), "unit": "Mpix/s", "ms": round(ms1, 1),
                                                     "kind": k1, "sample": d1}
+        # ... and on the B200 itself (SURVEY.md 8d "optional third line": reference modules + torch-eager stand-in)
+        try:
+            torch.cuda.empty_cache()
+            line["gpu_eager_reference"] = time_gpu_eager_reference(args.workload, dev)
+        except Exception as exc:
+            line["gpu_eager_reference"] = {"error": f"{type(exc).__name__}: {str(exc)[:200]}"}
+        torch.cuda.empty_cache()
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
