@@ -117,6 +117,45 @@ def test_naf_module_matches_reference_golden(name):
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+# ------------------------------------------------------------------ whole images against the reference itself
+@pytest.mark.parametrize("cfg", [("C1", 384, 16, 224, 224, 7), ("C2", 768, 32, 448, 896, 7), ("C3", 1024, 37, 518, 1036, 11),
+                                 ("C2 image at target size", 768, 32, 896, 896, 7)], ids=lambda c: c[0])
+def test_full_size_image_equals_the_reference_modules_on_the_same_gpu(cfg):
+    """One FULL-SIZE image of a BASELINE config through the UNMODIFIED reference modules (oracle/_ref: src/model/naf.py
+    NAF.forward, NATTEN's two functionals replaced by the pure-torch stand-in) run on this GPU in strict fp32, against
+    `naf_b200.NAF` with the same weights: every output element of the whole image, both precision classes of the
+    encoder.  (The CPU oracle is too slow at these sizes; this is the reference's own code on the same inputs.)"""
+    from oracle import reference_runner as R
+
+    if not R.available():
+        pytest.skip("oracle/_ref not built (python -m oracle.build_ref in the build container)")
+    name, C, lo, gi, to, K = cfg
+    torch.manual_seed(11)
+    ref = R.load().NAF(kernel_size=K).eval().to(dev())
+    ours = naf_b200.NAF(kernel_size=K).eval()
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev())
+    image, feats = rnd(21, 1, 3, gi, gi).to(dev()), rnd(22, 1, C, lo, lo).to(dev())
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        with torch.no_grad():
+            want = ref(image, feats, (to, to))
+            got = ours(image, feats, (to, to))          # strict class: split-fp16 three-pass encoder
+        assert got.shape == want.shape == (1, C, to, to)
+        err = (got - want).abs().max().item()
+        assert err <= 1e-4, (name, "strict", err)
+        torch.backends.cudnn.allow_tf32 = True            # PyTorch's default = what the bench runs
+        with torch.no_grad():
+            got_tf32 = ours(image, feats, (to, to))
+        err_tf32 = (got_tf32 - want).abs().max().item()
+        assert err_tf32 <= 1e-3, (name, "tf32 class", err_tf32)
+        print(f"{name}: max|ours - reference| strict {err:.2e}, tf32 class {err_tf32:.2e}")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ------------------------------------------------------------------ rectangular windows
 @pytest.mark.parametrize("name", G.names("rect_xattn_"))
 def test_rectangular_windows_match_reference_golden(name):
