@@ -208,3 +208,42 @@ def test_bf16_autocast_training_like_the_reference():
     out.float().pow(2).mean().backward()
     assert ft.grad is not None and ft.grad.dtype == torch.float32 and torch.isfinite(ft.grad).all()
     assert all(p.grad is not None for p in m.parameters())
+
+
+@pytest.mark.parametrize("cfg", [("C1", 384, 16, 224, 224, 7), ("training-like 32 <- 13", 384, 13, 56, 32, 9),
+                                 ("reference backward benchmark", 384, 28, 448, 448, 9)], ids=lambda c: c[0])
+def test_full_size_gradients_equal_the_reference_modules_on_the_same_gpu(cfg):
+    """Forward AND backward of one full-size image through the UNMODIFIED reference modules on this GPU (oracle/_ref,
+    autograd through the torch NATTEN stand-in, strict fp32) against `naf_b200.NAF` with the same weights: the output,
+    d features, d image and the gradient of every parameter (what train.py:136 back-propagates)."""
+    from oracle import reference_runner as R
+
+    if not R.available():
+        pytest.skip("oracle/_ref not built (python -m oracle.build_ref in the build container)")
+    name, C, lo, gi, to, K = cfg
+    torch.manual_seed(12)
+    ref = R.load().NAF(kernel_size=K).eval().to(dev())
+    ours = naf_b200.NAF(kernel_size=K).eval()
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(dev())
+    image, feats, dout = rnd(31, 1, 3, gi, gi).to(dev()), rnd(32, 1, C, lo, lo).to(dev()), rnd(33, 1, C, to, to).to(dev())
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        res = []
+        for model in (ref, ours):
+            img, ft = image.clone().requires_grad_(True), feats.clone().requires_grad_(True)
+            model.zero_grad()
+            out = model(img, ft, (to, to))
+            out.backward(dout)
+            res.append((out.detach(), img.grad, ft.grad, {n: p.grad for n, p in model.named_parameters()}))
+        (o_r, di_r, df_r, gp_r), (o_o, di_o, df_o, gp_o) = res
+        assert (o_o - o_r).abs().max().item() <= 1e-4
+        close(df_o, df_r.cpu(), (name, "dfeatures"), rel=1e-4)
+        close(di_o, di_r.cpu(), (name, "dimage"), rel=2e-4)
+        for n_, g in gp_r.items():
+            assert gp_o[n_] is not None, n_
+            close(gp_o[n_], g.cpu(), (name, n_), rel=3e-4)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

@@ -119,6 +119,7 @@ def test_naf_module_matches_reference_golden(name):
 
 # ------------------------------------------------------------------ whole images against the reference itself
 @pytest.mark.parametrize("cfg", [("C1", 384, 16, 224, 224, 7), ("C2", 768, 32, 448, 896, 7), ("C3", 1024, 37, 518, 1036, 11),
+                                 ("C4", 768, 24, 336, 1344, 7), ("C5", 768, 32, 512, 2048, 7),
                                  ("C2 image at target size", 768, 32, 896, 896, 7)], ids=lambda c: c[0])
 def test_full_size_image_equals_the_reference_modules_on_the_same_gpu(cfg):
     """One FULL-SIZE image of a BASELINE config through the UNMODIFIED reference modules (oracle/_ref: src/model/naf.py
