@@ -32,24 +32,51 @@ namespace naf {
 
 using namespace umma;
 
+#if NAF_BWD_EXP & 32
+// profiling build only: clock stamps of thread 0 of four CTAs at every phase boundary (scripts/trace_bwd.py)
+__device__ long long g_bwd_trace[4][128];
+#define NAF_TR()                                                        \
+  do {                                                                  \
+    if (tid == 0 && tr_slot >= 0 && tr_i < 128) g_bwd_trace[tr_slot][tr_i++] = clock64(); \
+  } while (0)
+#else
+#define NAF_TR() do { } while (0)
+#endif
+
 namespace {
 
 constexpr int DQ = 64;        // head dim of q / k
 constexpr int KC = DQ / 8;    // 16-byte chunks along a 64-channel operand row
-constexpr int NT = 256;
+constexpr int NW = 256;       // worker threads: two per pixel row (TMEM lane)
+constexpr int NT = NW + 128;  // + the MMA warp group (one issuing thread; a whole warp group so that setmaxnreg applies)
 constexpr int DVC = 64;       // value channels per chunk
 constexpr int PIXIMG = KC * 128 * 16;   // one fp16 image of a 128 x 64 pixel-major operand (16 KB)
-constexpr int TIMG = 128 * 128 * 2;     // P^T / dS^T image: 128 taps x 128 pixels fp16 (32 KB)
 
 template <int TP>
 struct BwdCfg {
   static constexpr int kWin = KC * TP * 16;   // one fp16 image of a TP x 64 window operand
-  static constexpr int kSmem = 4 * kWin + 4 * PIXIMG + 2 * TIMG;   // K, V chunk (hi, lo); Q, G chunk (hi, lo); T (hi, lo)
+  // P^T / dS^T image: TP taps x 128 pixels fp16, [pixel group of 8][tap group of 8][pixel % 8][8 taps]; kPG = bytes
+  // per pixel group.  The M = 128 MMAs that read it as their A operand run over tap groups TP/8 .. 15 into whatever
+  // follows (the next pixel group, and past the last one the K window, which is why T comes first in shared
+  // memory): finite fp16 bits that only reach accumulator lanes >= TP, which nothing ever reads.
+  static constexpr int kPG = TP * 16;
+  static constexpr int kT = 16 * kPG;
   static constexpr int kTA = (TP + 31) / 32 * 32;                   // TMEM regions start on 32-column boundaries
 };
 
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// n / d for 0 <= n, n * d < 2^32, with magic = ceil(2^32 / d) computed on the host (d = 1: no magic number fits)
+__host__ __device__ __forceinline__ uint32_t magic_of(int d) { return d > 1 ? uint32_t(((1ull << 32) + uint32_t(d) - 1) / uint32_t(d)) : 0u; }
+__device__ __forceinline__ int magic_div(int n, int d, uint32_t magic) { return d > 1 ? int(__umulhi(uint32_t(n), magic)) : n; }
+
+// 32-byte global load that stays where it is written (register prefetch: the compiler must not sink it to its use)
+__device__ __forceinline__ void ldg8_keep(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
 }
 
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo) {
@@ -61,33 +88,47 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 
 }  // namespace
 
+// Barriers of the hand-off protocol (one CTA): "ready" barriers collect one arrival per worker thread, "done"
+// barriers are tcgen05.commit targets.  Every waiter waits every phase of its barriers at least once and never
+// skips one; a wait may be repeated as long as nothing has committed / arrived on the barrier in between.
+struct BwdBars {
+  uint64_t q_ready[2];    // Q of a tile staged in Q buffer i            (workers -> MMA thread)
+  uint64_t s_done[2];     // S of a tile complete in S region i          (tensor core -> workers)
+  uint64_t pt_ready;      // P^T of the tile written                     (workers -> MMA thread)
+  uint64_t g_ready[2];    // upstream-gradient chunk staged in G buffer  (workers -> MMA thread)
+  uint64_t g_done[2];     // dP / dVw MMAs of a chunk step complete      (tensor core -> workers)
+  uint64_t ds_ready;      // dS in TMEM, dS^T in shared memory           (workers -> MMA thread)
+  uint64_t dq_done;       // dQ / dKw of the tile complete               (tensor core -> workers)
+};
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
+
 template <int TP>
 __global__ void __launch_bounds__(NT, 1)
-xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_resident) {
+xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_resident, int gbufs, int overlap,
+                         uint32_t m_rw, uint32_t m_ry, uint32_t m_rx) {
   using Cfg = BwdCfg<TP>;
   constexpr int SC = TP / 2;   // S / dP columns per thread
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t mbar;
+  __shared__ BwdBars bars;
   __shared__ uint32_t tmem_base_s;
   __shared__ float red_a[2][128];
   __shared__ float red_b[2][128];
 
-  uint8_t* sKhi = smem;
+  uint8_t* sThi = smem;               // P^T, then dS^T: MN-major A images
+  uint8_t* sTlo = sThi + Cfg::kT;
+  uint8_t* sKhi = sTlo + Cfg::kT;
   uint8_t* sKlo = sKhi + Cfg::kWin;
   // V window: [channel group][tap][16 B]; the whole value head when it fits (staged once per cell), else one
   // 64-channel chunk restaged per tile and chunk
   const int v_img = (v_resident ? (dv >> 3) : KC) * TP * 16;
   uint8_t* sVhi = sKlo + Cfg::kWin;
   uint8_t* sVlo = sVhi + v_img;
-  uint8_t* sQhi = sVlo + v_img;
-  uint8_t* sQlo = sQhi + PIXIMG;
-  uint8_t* sGhi = sQlo + PIXIMG;
-  uint8_t* sGlo = sGhi + PIXIMG;
-  uint8_t* sThi = sGlo + PIXIMG;      // P^T, then dS^T: MN-major A images [pixel group][tap group][pixel % 8][8 taps]
-  uint8_t* sTlo = sThi + TIMG;
+  uint8_t* sQ = sVlo + v_img;                              // (1 + overlap) x (hi, lo) images of the rotated queries
+  uint8_t* sG = sQ + (1 + overlap) * (2 * PIXIMG);         // gbufs x (hi, lo) images of the upstream-gradient chunk
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rowgrp = warp & 3, hf = warp >> 2;
+  const int rowgrp = warp & 3, hf = (warp >> 2) & 1;
   const int row = rowgrp * 32 + lane;
   const int K = p.K, K2 = K * K;
 
@@ -100,40 +141,26 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   const int b = bid / p.h;
   const int wy0 = window_origin(ci, p.h, K), wx0 = window_origin(cj, p.w, K);
 
+#if NAF_BWD_EXP & 32
+  const int tr_slot = blockIdx.x == gridDim.x / 4 ? 0 : blockIdx.x == gridDim.x / 2 ? 1 : blockIdx.x == gridDim.x / 4 * 3 ? 2 : blockIdx.x == gridDim.x - 200 ? 3 : -1;
+  int tr_i = 0;
+#endif
+  NAF_TR();   // 0: CTA start
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    mbar_init(&mbar, 1);
+    mbar_init(&bars.q_ready[0], NW);
+    mbar_init(&bars.q_ready[1], NW);
+    mbar_init(&bars.s_done[0], 1);
+    mbar_init(&bars.s_done[1], 1);
+    mbar_init(&bars.pt_ready, NW);
+    mbar_init(&bars.g_ready[0], NW);
+    mbar_init(&bars.g_ready[1], NW);
+    mbar_init(&bars.g_done[0], 1);
+    mbar_init(&bars.g_done[1], 1);
+    mbar_init(&bars.ds_ready, NW);
+    mbar_init(&bars.dq_done, 1);
     fence_mbar_init();
   }
-  // P^T / dS^T images: tap rows >= TP are never written; they must read as zeros (M = 128 always)
-  for (int i = tid; i < 2 * TIMG / 16; i += NT) reinterpret_cast<uint4*>(sThi)[i] = make_uint4(0, 0, 0, 0);
-  // K window: K-major [channel chunk c][tap n][16 B], zero rows for the padding taps
-  const float* kwin = p.k + (int64_t(b * p.h + wy0) * p.w + wx0) * p.D + head * DQ;
-  for (int i = tid; i < TP * KC; i += NT) {
-    const int n = i % TP, c = i / TP;
-    uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-    if (n < K2) {
-      const int t = n / K, u = n - t * K;
-      float x[8];
-      const float4* src = reinterpret_cast<const float4*>(kwin + (int64_t(t) * p.w + u) * p.D + c * 8);
-      const float4 a = __ldg(src), bb = __ldg(src + 1);
-      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bb.x; x[5] = bb.y; x[6] = bb.z; x[7] = bb.w;
-      split8(x, hi, lo);
-    }
-    *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
-    *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
-  }
-  fence_before_sync();
-  __syncthreads();
-  fence_after_sync();
-
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
-  const uint32_t tS = tmem;                  // S, later dS (fp16 hi | lo)
-  const uint32_t tdP = tmem + Cfg::kTA;      // dP, later dQ (64 columns)
-  const uint32_t tdK = tdP + (Cfg::kTA > DQ ? Cfg::kTA : DQ);   // dKw accumulator (taps x 64)
-  const uint32_t tdV = tdK + DQ;             // dVw accumulator (taps x dv)
-
   const bool rope = p.cos_y != nullptr;
   const float qscale = p.scale * 1.4426950408889634f;
   const int npix = rh * rw;
@@ -141,7 +168,6 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   const int nchunks = (dv + DVC - 1) / DVC;
   const int y0 = ci * rh, x0 = cj * rw;
   const float* vwin = p.v + (int64_t(b * p.h + wy0) * p.w + wx0) * p.C + head * dv;
-  uint32_t phase = 0;
   constexpr uint32_t idesc_s = make_idesc_f16(128, TP, false, false);     // S, dP: A K-major, B K-major
   constexpr uint32_t idesc_dq = make_idesc_f16(128, DQ, false, true);     // dQ: A in TMEM, B MN-major
   constexpr uint32_t idesc_dk = make_idesc_f16(128, DQ, true, true);      // dKw: A MN-major, B MN-major
@@ -153,301 +179,402 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
     Px r;
     const int pi = tile * 128 + row;
     r.valid = tile < ntiles && pi < npix;
-    const int py = r.valid ? pi / rw : 0;
+    const int py = r.valid ? magic_div(pi, rw, m_rw) : 0;
     r.y = y0 + py;
     r.x = x0 + (r.valid ? pi - py * rw : 0);
     r.pix = (int64_t(b) * p.Ho + r.y) * p.Wo + r.x;
     return r;
   };
-  float4 qa4[4], qb4[4];     // hf 0 owns rotation pairs 0..15 (channels 0..15 / 32..47, row angles), hf 1 pairs 16..31
-  auto load_q = [&](const Px& px) {
-    if (px.valid) {
-      const float* qp = p.q + int64_t(b) * p.q_stride_b + int64_t(px.y / p.rep_y) * p.q_stride_y +
-                        int64_t(px.x / p.rep_x) * p.q_stride_x + head * DQ + 16 * hf;
+  // Global loads are laid out for the memory pipeline, not for the TMEM lanes: one warp instruction reads 8 pixels x
+  // 128 contiguous bytes (lane = pixel % 8 + 8 * (32-byte piece)), i.e. 8 full lines, where a row-per-thread mapping
+  // touches 32 lines for the same bytes (measured: the load / store unit's request rate bounded the whole kernel).
+  // The operand images in shared memory are indexed by (channel group, pixel), so any thread may stage any element,
+  // and 8 consecutive lanes write 8 consecutive pixels of one group: conflict-free.
+  const int lp = lane & 7, lg = lane >> 3;
+  auto pix_of = [&](int tile, int P, int& y, int& x) -> bool {     // tile-local pixel P -> target coordinates
+    const int pi = tile * 128 + P;
+    const bool valid = tile < ntiles && pi < npix;
+    const int py = valid ? magic_div(pi, rw, m_rw) : 0;
+    y = y0 + py;
+    x = x0 + (valid ? pi - py * rw : 0);
+    return valid;
+  };
+  float qa8[2][8], qb8[2][8];     // pixel (k * 8 + warp) * 8 + lp: channels lg * 8 .. + 7 and their rotation partners (+ 32)
+  auto load_q = [&](int tile) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        qa4[j] = ldg_stream(qp + 4 * j);
-        qb4[j] = ldg_stream(qp + 32 + 4 * j);
+    for (int k = 0; k < 2; ++k) {
+      int y, x;
+      if (pix_of(tile, (k * 8 + warp) * 8 + lp, y, x)) {
+        const float* qp = p.q + int64_t(b) * p.q_stride_b + int64_t(magic_div(y, p.rep_y, m_ry)) * p.q_stride_y +
+                          int64_t(magic_div(x, p.rep_x, m_rx)) * p.q_stride_x + head * DQ + lg * 8;
+        ldg8_keep(qp, qa8[k]);
+        ldg8_keep(qp + 32, qb8[k]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qa8[k][e] = qb8[k][e] = 0.f;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) qa4[j] = qb4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  float4 g4[4][2];           // channel groups hf, hf + 2, hf + 4, hf + 6 of this pixel's chunk
-  auto load_g = [&](const Px& px, int c) {
+  float g8r[4][8];           // block k * 8 + warp of the chunk: 8 pixels x one quad of channel groups
+  auto load_g = [&](int tile, int c) {
     const int ng = min(DVC, dv - c * DVC) >> 3;
-    const float* gp = p.dout + px.pix * p.C + head * dv + c * DVC;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int g8 = hf + 2 * k;
-      if (px.valid && g8 < ng && !(NAF_BWD_EXP & 16)) {
-        g4[k][0] = ldg_stream(gp + g8 * 8);
-        g4[k][1] = ldg_stream(gp + g8 * 8 + 4);
+      const int bi = k * 8 + warp, g = (bi >> 4) * 4 + lg;
+      int y, x;
+      const bool valid = pix_of(tile, (bi & 15) * 8 + lp, y, x);
+      if (valid && g < ng && !(NAF_BWD_EXP & 16)) {
+        ldg8_keep(p.dout + ((int64_t(b) * p.Ho + y) * p.Wo + x) * p.C + head * dv + c * DVC + g * 8, g8r[k]);
       } else {
-        g4[k][0] = g4[k][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g8r[k][e] = 0.f;
       }
     }
   };
-  Px cur = px_of(0);
-  load_q(cur);
-  load_g(cur, 0);
-
-  for (int tile = 0; tile < ntiles; ++tile) {
-    const Px nxt = px_of(tile + 1);
-    // ================= stage Q (rotated, unscaled): K-major [chunk][row][16 B]
-    {
-      float qa[16], qb[16];
+  // rotated, unscaled queries of a tile: K-major [chunk][row][16 B] hi / lo images
+  auto stage_q = [&](int tile, uint8_t* sQhi) {
+    uint8_t* const sQlo = sQhi + PIXIMG;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        qa[4 * j] = qa4[j].x; qa[4 * j + 1] = qa4[j].y; qa[4 * j + 2] = qa4[j].z; qa[4 * j + 3] = qa4[j].w;
-        qb[4 * j] = qb4[j].x; qb[4 * j + 1] = qb4[j].y; qb[4 * j + 2] = qb4[j].z; qb[4 * j + 3] = qb4[j].w;
-      }
-      if (rope && cur.valid) {
-        const float4* ct = reinterpret_cast<const float4*>(hf == 0 ? p.cos_y + int64_t(cur.y) * 16 : p.cos_x + int64_t(cur.x) * 16);
-        const float4* st = reinterpret_cast<const float4*>(hf == 0 ? p.sin_y + int64_t(cur.y) * 16 : p.sin_x + int64_t(cur.x) * 16);
+    for (int k = 0; k < 2; ++k) {
+      const int P = (k * 8 + warp) * 8 + lp;
+      int y, x;
+      if (pix_of(tile, P, y, x) && rope) {
+        // rotation pair j = lg * 8 + e: row angles for j < 16, column angles above
+        const float* ct = lg < 2 ? p.cos_y + int64_t(y) * 16 + lg * 8 : p.cos_x + int64_t(x) * 16 + (lg - 2) * 8;
+        const float* st = lg < 2 ? p.sin_y + int64_t(y) * 16 + lg * 8 : p.sin_x + int64_t(x) * 16 + (lg - 2) * 8;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 c4 = __ldg(ct + j), s4 = __ldg(st + j);
+        for (int j = 0; j < 2; ++j) {
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(ct) + j), s4 = __ldg(reinterpret_cast<const float4*>(st) + j);
           const float c[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = qa[4 * j + e], bb = qb[4 * j + e];
-            qa[4 * j + e] = a * c[e] - bb * sn[e];
-            qb[4 * j + e] = bb * c[e] + a * sn[e];
+            const float a = qa8[k][4 * j + e], bb = qb8[k][4 * j + e];
+            qa8[k][4 * j + e] = a * c[e] - bb * sn[e];
+            qb8[k][4 * j + e] = bb * c[e] + a * sn[e];
           }
         }
       }
       uint4 hi, lo;
-      split8(*reinterpret_cast<float(*)[8]>(&qa[0]), hi, lo);
-      *reinterpret_cast<uint4*>(sQhi + ((2 * hf) * 128 + row) * 16) = hi;
-      *reinterpret_cast<uint4*>(sQlo + ((2 * hf) * 128 + row) * 16) = lo;
-      split8(*reinterpret_cast<float(*)[8]>(&qa[8]), hi, lo);
-      *reinterpret_cast<uint4*>(sQhi + ((2 * hf + 1) * 128 + row) * 16) = hi;
-      *reinterpret_cast<uint4*>(sQlo + ((2 * hf + 1) * 128 + row) * 16) = lo;
-      split8(*reinterpret_cast<float(*)[8]>(&qb[0]), hi, lo);
-      *reinterpret_cast<uint4*>(sQhi + ((4 + 2 * hf) * 128 + row) * 16) = hi;
-      *reinterpret_cast<uint4*>(sQlo + ((4 + 2 * hf) * 128 + row) * 16) = lo;
-      split8(*reinterpret_cast<float(*)[8]>(&qb[8]), hi, lo);
-      *reinterpret_cast<uint4*>(sQhi + ((5 + 2 * hf) * 128 + row) * 16) = hi;
-      *reinterpret_cast<uint4*>(sQlo + ((5 + 2 * hf) * 128 + row) * 16) = lo;
+      split8(qa8[k], hi, lo);
+      *reinterpret_cast<uint4*>(sQhi + (lg * 128 + P) * 16) = hi;
+      *reinterpret_cast<uint4*>(sQlo + (lg * 128 + P) * 16) = lo;
+      split8(qb8[k], hi, lo);
+      *reinterpret_cast<uint4*>(sQhi + ((lg + 4) * 128 + P) * 16) = hi;
+      *reinterpret_cast<uint4*>(sQlo + ((lg + 4) * 128 + P) * 16) = lo;
     }
-    load_q(nxt);     // in flight during the whole tile
+  };
+
+  Px cur = px_of(0);
+  if (warp < NW / 32) {
+    load_q(0);
+    load_g(0, 0);
+    // K window: K-major [channel chunk c][tap n][16 B], zero rows for the padding taps
+    const float* kwin = p.k + (int64_t(b * p.h + wy0) * p.w + wx0) * p.D + head * DQ;
+    for (int i = tid; i < TP * KC; i += NW) {
+      const int n = i % TP, c = i / TP;
+      uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+      if (n < K2) {
+        const int t = n / K, u = n - t * K;
+        float x[8];
+        const float4* src = reinterpret_cast<const float4*>(kwin + (int64_t(t) * p.w + u) * p.D + c * 8);
+        const float4 a = __ldg(src), bb = __ldg(src + 1);
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bb.x; x[5] = bb.y; x[6] = bb.z; x[7] = bb.w;
+        split8(x, hi, lo);
+      }
+      *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
+      *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
+    }
     fence_proxy_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      // S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a0 = smem_u32(pass == 1 ? sQlo : sQhi);
-        const uint32_t b0 = smem_u32(pass == 2 ? sKlo : sKhi);
-#pragma unroll
-        for (int ks = 0; ks < DQ / 16; ++ks)
-          mma_f16_ss(tS, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
-                     make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (pass | ks) != 0);
-      }
-      commit(&mbar);
-    }
-    mbar_wait(&mbar, phase);
-    phase ^= 1;
-    fence_after_sync();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  NAF_TR();   // 1: prologue done
 
-    // ================= P = softmax(scale S) on this thread's half row; P^T (fp16 hi / lo) -> shared memory
-    float pr[SC];
-    const int tap0 = hf * SC;
-    uint8_t* const tdst = sThi + (row >> 3) * 2048 + (tap0 >> 3) * 128 + (row & 7) * 16;
-    {
-      uint32_t s[SC];
-#pragma unroll
-      for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(tS + lane_off + hf * SC + c0, *reinterpret_cast<uint32_t(*)[8]>(&s[c0]));
-      wait_ld();
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < SC; ++j)
-        if (tap0 + j < K2) m = fmaxf(m, __uint_as_float(s[j]));
-      red_a[hf][row] = m;
-      fence_before_sync();
-      __syncthreads();
-      fence_after_sync();
-      const float mq = fmaxf(red_a[0][row], red_a[1][row]) * qscale;
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < SC; ++j) {
-        const float e = (tap0 + j < K2) ? fast_exp2(fmaf(__uint_as_float(s[j]), qscale, -mq)) : 0.f;
-        pr[j] = e;
-        l += e;
-      }
-      red_b[hf][row] = l;
-      __syncthreads();
-      const float inv = 1.f / (red_b[0][row] + red_b[1][row]);
-#pragma unroll
-      for (int j = 0; j < SC; ++j) pr[j] *= inv;
-#pragma unroll
-      for (int g8 = 0; g8 < SC / 8; ++g8) {
-        uint4 hi, lo;
-        split8(*reinterpret_cast<float(*)[8]>(&pr[8 * g8]), hi, lo);
-        *reinterpret_cast<uint4*>(tdst + g8 * 128) = hi;
-        *reinterpret_cast<uint4*>(tdst + TIMG + g8 * 128) = lo;
-      }
-    }
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_off = uint32_t(rowgrp * 32) << 16;
+  // TMEM: S (later dS, fp16 hi | lo) x (1 + overlap) | dP (later dQ) | dKw (taps x 64) | dVw (taps x dv)
+  const uint32_t tS0 = tmem;
+  const uint32_t tdP = tmem + (1 + overlap) * Cfg::kTA;
+  const uint32_t tdK = tdP + (Cfg::kTA > DQ ? Cfg::kTA : DQ);
+  const uint32_t tdV = tdK + DQ;
+  // buffer / barrier index and wait parity of tile t (Q images, S regions) and of chunk step s (G images)
+  auto tb = [&](int t) { return overlap ? (t & 1) : 0; };
+  auto tpar = [&](int t) { return uint32_t(overlap ? (t >> 1) & 1 : t & 1); };
+  auto gb = [&](int s) { return gbufs == 2 ? (s & 1) : 0; };
+  auto gpar = [&](int s) { return uint32_t(gbufs == 2 ? (s >> 1) & 1 : s & 1); };
 
-    // ================= value-head chunks: dP += G_c Vw_c^T,  dVw[:, chunk c] += P^T G_c
-    for (int c = 0; c < nchunks; ++c) {
-      const int wc = min(DVC, dv - c * DVC);          // channels in this chunk (multiple of 16)
-      // G chunk (prefetched): K-major [channel group][row][16 B]
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int g8 = hf + 2 * k;
-        if (g8 < (wc >> 3)) {
-          const float x[8] = {g4[k][0].x, g4[k][0].y, g4[k][0].z, g4[k][0].w, g4[k][1].x, g4[k][1].y, g4[k][1].z, g4[k][1].w};
-          uint4 hi, lo;
-          split8(x, hi, lo);
-          *reinterpret_cast<uint4*>(sGhi + (g8 * 128 + row) * 16) = hi;
-          *reinterpret_cast<uint4*>(sGlo + (g8 * 128 + row) * 16) = lo;
-        }
-      }
-      if (c + 1 < nchunks) load_g(cur, c + 1);
-      else if (tile + 1 < ntiles) load_g(nxt, 0);
-      // V window chunk: K-major [channel group][tap][16 B] (once per cell when the head is one chunk wide)
-      uint8_t* const vhi = sVhi + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
-      uint8_t* const vlo = sVlo + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
-      if (tile == 0 || !v_resident) {
-        constexpr int VIT = (TP * 8 + NT - 1) / NT;     // items per thread at the full chunk width
-        float4 va[VIT], vb[VIT];
-#pragma unroll
-        for (int k = 0; k < VIT; ++k) {
-          const int i = tid + k * NT;
-          const int n = i % TP, g8 = i / TP;
-          va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (g8 < (wc >> 3) && n < K2) {
-            const int t = n / K, u = n - t * K;
-            const float4* src = reinterpret_cast<const float4*>(vwin + (int64_t(t) * p.w + u) * p.C + c * DVC + g8 * 8);
-            va[k] = __ldg(src);
-            vb[k] = __ldg(src + 1);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < VIT; ++k) {
-          const int i = tid + k * NT;
-          const int n = i % TP, g8 = i / TP;
-          if (g8 < (wc >> 3)) {
-            const float x[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
-            uint4 hi, lo;
-            split8(x, hi, lo);
-            *reinterpret_cast<uint4*>(vhi + (g8 * TP + n) * 16) = hi;
-            *reinterpret_cast<uint4*>(vlo + (g8 * TP + n) * 16) = lo;
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+  if (warp >= NW / 32) {
+    // ================================================================ MMA thread
+    // 12 warps start with 168 registers each; this group hands its share to the workers
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    if (warp == NW / 32 && lane == 0) {
+      auto issue_s = [&](int t) {
+        // S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T
+        mbar_wait(&bars.q_ready[tb(t)], tpar(t));
         fence_after_sync();
-        // dP (+)= Ghi Vhi^T + Glo Vhi^T + Ghi Vlo^T
+        const uint32_t qhi = smem_u32(sQ + tb(t) * (2 * PIXIMG)), qlo = qhi + PIXIMG;
+#pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = smem_u32(pass == 1 ? sGlo : sGhi);
-          const uint32_t b0 = smem_u32(pass == 2 ? vlo : vhi);
-          for (int ks = 0; ks < (wc >> 4); ++ks)
-            if (!(NAF_BWD_EXP & 4)) mma_f16_ss(tdP, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
-                       make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (c | pass | ks) != 0);
+          const uint32_t a0 = pass == 1 ? qlo : qhi;
+          const uint32_t b0 = smem_u32(pass == 2 ? sKlo : sKhi);
+#pragma unroll
+          for (int ks = 0; ks < DQ / 16; ++ks)
+            mma_f16_ss(tS0 + tb(t) * Cfg::kTA, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
+                       make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (pass | ks) != 0);
         }
-        // dVw[:, chunk] (+)= P^T_hi Ghi + P^T_lo Ghi + P^T_hi Glo   (A = P^T MN-major, B = G seen MN-major: K = pixels)
-        const uint32_t idesc_dv = make_idesc_f16(128, wc, true, true);
+        commit(&bars.s_done[tb(t)]);
+      };
+      issue_s(0);
+      int s = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        for (int c = 0; c < nchunks; ++c, ++s) {
+          const int wc = min(DVC, dv - c * DVC);
+          const uint32_t ghi = smem_u32(sG + gb(s) * (2 * PIXIMG)), glo = ghi + PIXIMG;
+          const uint32_t vhi = smem_u32(sVhi + (v_resident ? c * (DVC / 8) * TP * 16 : 0));
+          const uint32_t vlo = smem_u32(sVlo + (v_resident ? c * (DVC / 8) * TP * 16 : 0));
+          mbar_wait(&bars.g_ready[gb(s)], gpar(s));
+          fence_after_sync();
+          // dP (+)= Ghi Vhi^T + Glo Vhi^T + Ghi Vlo^T
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a0 = pass == 1 ? glo : ghi;
+            const uint32_t b0 = pass == 2 ? vlo : vhi;
+            for (int ks = 0; ks < (wc >> 4); ++ks)
+              if (!(NAF_BWD_EXP & 4)) mma_f16_ss(tdP, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
+                         make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (c | pass | ks) != 0);
+          }
+          if (c == 0) {
+            mbar_wait(&bars.pt_ready, t & 1);
+            fence_after_sync();
+          }
+          // dVw[:, chunk] (+)= P^T_hi Ghi + P^T_lo Ghi + P^T_hi Glo   (A = P^T MN-major, B = G seen MN-major: K = pixels)
+          const uint32_t idesc_dv = make_idesc_f16(128, wc, true, true);
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a0 = smem_u32(pass == 1 ? sTlo : sThi);
+            const uint32_t b0 = pass == 2 ? glo : ghi;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              if (!(NAF_BWD_EXP & 1)) mma_f16_ss(tdV + c * DVC, make_desc(a0 + ks * 2 * Cfg::kPG, Cfg::kPG, 128),
+                         make_desc(b0 + ks * 2 * 128, 128, 128 * 16), idesc_dv, (t | pass | ks) != 0);
+          }
+          commit(&bars.g_done[gb(s)]);
+        }
+        mbar_wait(&bars.ds_ready, t & 1);
+        fence_after_sync();
+        const uint32_t tS = tS0 + tb(t) * Cfg::kTA;
+        const uint32_t qhi = smem_u32(sQ + tb(t) * (2 * PIXIMG)), qlo = qhi + PIXIMG;
+        // dQ = dShi Khi + dSlo Khi + dShi Klo      (B = the K window seen MN-major: N = channels, K = taps)
+#pragma unroll
+        for (int pass = 0; pass < 3; ++pass) {
+          const uint32_t a0 = tS + (pass == 1 ? TP / 2 : 0);
+          const uint32_t b0 = smem_u32(pass == 2 ? sKlo : sKhi);
+#pragma unroll
+          for (int ks = 0; ks < TP / 16; ++ks)
+            mma_f16_ts(tdP, a0 + ks * 8, make_desc(b0 + ks * 2 * 128, 128, TP * 16), idesc_dq, (pass | ks) != 0);
+        }
+        // dKw (+)= dS^T_hi Qhi + dS^T_lo Qhi + dS^T_hi Qlo
+#pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a0 = smem_u32(pass == 1 ? sTlo : sThi);
-          const uint32_t b0 = smem_u32(pass == 2 ? sGlo : sGhi);
+          const uint32_t b0 = pass == 2 ? qlo : qhi;
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            if (!(NAF_BWD_EXP & 1)) mma_f16_ss(tdV + c * DVC, make_desc(a0 + ks * 2 * 2048, 2048, 128),
-                       make_desc(b0 + ks * 2 * 128, 128, 128 * 16), idesc_dv, (tile | pass | ks) != 0);
+            if (!(NAF_BWD_EXP & 2)) mma_f16_ss(tdK, make_desc(a0 + ks * 2 * Cfg::kPG, Cfg::kPG, 128), make_desc(b0 + ks * 2 * 128, 128, 128 * 16),
+                       idesc_dk, (t | pass | ks) != 0);
         }
-        commit(&mbar);
+        commit(&bars.dq_done);
+        if (t + 1 < ntiles) issue_s(t + 1);
       }
-      mbar_wait(&mbar, phase);
-      phase ^= 1;
-      fence_after_sync();
     }
+    __syncwarp();
+  } else {
+    // ================================================================ workers: two threads per pixel row
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int tap0 = hf * SC;
+    uint8_t* const tdst = sThi + (row >> 3) * Cfg::kPG + (tap0 >> 3) * 128 + (row & 7) * 16;
+    auto next_q = [&](int t) {      // stage the queries of tile t, start loading those of tile t + 1
+      stage_q(t, sQ + tb(t) * (2 * PIXIMG));
+      load_q(t + 1);
+      fence_proxy_async_smem();
+      mbar_arrive(&bars.q_ready[tb(t)]);
+    };
+    next_q(0);
+    int gstep = 0;
+    for (int tile = 0; tile < ntiles; ++tile) {
+      const Px nxt = px_of(tile + 1);
+      float pr[SC];
+      // ================= value-head chunks: dP += G_c Vw_c^T,  dVw[:, chunk c] += P^T G_c
+      for (int c = 0; c < nchunks; ++c, ++gstep) {
+        const int wc = min(DVC, dv - c * DVC);          // channels in this chunk (multiple of 16)
+        uint8_t* const sGhi = sG + gb(gstep) * (2 * PIXIMG);
+        uint8_t* const sGlo = sGhi + PIXIMG;
+        // the MMAs that read this G buffer (step gstep - gbufs) must have completed; with one buffer this also frees
+        // the V chunk buffer of a value head that is not resident
+        if (gstep >= gbufs) mbar_wait(&bars.g_done[gb(gstep - gbufs)], gpar(gstep - gbufs));
+        // G chunk (prefetched): K-major [channel group][row][16 B]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int bi = k * 8 + warp, g8 = (bi >> 4) * 4 + lg;
+          if (g8 < (wc >> 3)) {
+            uint4 hi, lo;
+            split8(g8r[k], hi, lo);
+            *reinterpret_cast<uint4*>(sGhi + (g8 * 128 + (bi & 15) * 8 + lp) * 16) = hi;
+            *reinterpret_cast<uint4*>(sGlo + (g8 * 128 + (bi & 15) * 8 + lp) * 16) = lo;
+          }
+        }
+        if (c + 1 < nchunks) load_g(tile, c + 1);
+        else if (tile + 1 < ntiles) load_g(tile + 1, 0);
+        // V window chunk: K-major [channel group][tap][16 B] (once per cell when the value head is resident)
+        if (tile == 0 || !v_resident) {
+          uint8_t* const vhi = sVhi + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
+          uint8_t* const vlo = sVlo + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
+          constexpr int VIT = (TP * 8 + NW - 1) / NW;     // items per thread at the full chunk width
+          float4 va[VIT], vb[VIT];
+#pragma unroll
+          for (int k = 0; k < VIT; ++k) {
+            const int i = tid + k * NW;
+            const int n = i % TP, g8 = i / TP;
+            va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g8 < (wc >> 3) && n < K2) {
+              const int t = n / K, u = n - t * K;
+              const float4* src = reinterpret_cast<const float4*>(vwin + (int64_t(t) * p.w + u) * p.C + c * DVC + g8 * 8);
+              va[k] = __ldg(src);
+              vb[k] = __ldg(src + 1);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < VIT; ++k) {
+            const int i = tid + k * NW;
+            const int n = i % TP, g8 = i / TP;
+            if (g8 < (wc >> 3)) {
+              const float x[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              *reinterpret_cast<uint4*>(vhi + (g8 * TP + n) * 16) = hi;
+              *reinterpret_cast<uint4*>(vlo + (g8 * TP + n) * 16) = lo;
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars.g_ready[gb(gstep)]);
+        NAF_TR();   // D: chunk staged
 
-    // ================= dS = scale P (dP - delta): TMEM (A operand of dQ, hi | lo) and dS^T -> the T buffer
-    {
-      uint32_t d[SC];
+        if (c == 0) {
+          // ================= P = softmax(scale S) on this thread's half row; P^T (fp16 hi / lo) -> shared memory
+          // (the tensor core runs dP of chunk 0 meanwhile)
+          mbar_wait(&bars.s_done[tb(tile)], tpar(tile));
+          fence_after_sync();
+          NAF_TR();   // B: S complete
+          uint32_t sv[SC];
 #pragma unroll
-      for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(tdP + lane_off + hf * SC + c0, *reinterpret_cast<uint32_t(*)[8]>(&d[c0]));
-      wait_ld();
-      float dl = 0.f;
+          for (int c0 = 0; c0 < SC; c0 += 8)
+            tmem_ld8(tS0 + tb(tile) * Cfg::kTA + lane_off + hf * SC + c0, *reinterpret_cast<uint32_t(*)[8]>(&sv[c0]));
+          wait_ld();
+          float m = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < SC; ++j) dl = fmaf(pr[j], __uint_as_float(d[j]), dl);
-      red_a[hf][row] = dl;
-      fence_before_sync();   // dP was read: dQ may overwrite it after the barriers below
-      __syncthreads();
+          for (int j = 0; j < SC; ++j)
+            if (tap0 + j < K2) m = fmaxf(m, __uint_as_float(sv[j]));
+          red_a[hf][row] = m;
+          worker_sync();
+          const float mq = fmaxf(red_a[0][row], red_a[1][row]) * qscale;
+          float l = 0.f;
+#pragma unroll
+          for (int j = 0; j < SC; ++j) {
+            const float e = (tap0 + j < K2) ? fast_exp2(fmaf(__uint_as_float(sv[j]), qscale, -mq)) : 0.f;
+            pr[j] = e;
+            l += e;
+          }
+          red_b[hf][row] = l;
+          worker_sync();
+          const float inv = 1.f / (red_b[0][row] + red_b[1][row]);
+#pragma unroll
+          for (int j = 0; j < SC; ++j) pr[j] *= inv;
+#pragma unroll
+          for (int g8 = 0; g8 < SC / 8; ++g8) {
+            uint4 hi, lo;
+            split8(*reinterpret_cast<float(*)[8]>(&pr[8 * g8]), hi, lo);
+            *reinterpret_cast<uint4*>(tdst + g8 * 128) = hi;
+            *reinterpret_cast<uint4*>(tdst + Cfg::kT + g8 * 128) = lo;
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&bars.pt_ready);
+          NAF_TR();   // C: softmax, P^T written
+        }
+      }
+      // dP is complete and P^T may be overwritten once every chunk step of the tile has completed
+      if (gbufs == 2 && gstep >= 2) mbar_wait(&bars.g_done[gb(gstep - 2)], gpar(gstep - 2));
+      mbar_wait(&bars.g_done[gb(gstep - 1)], gpar(gstep - 1));
       fence_after_sync();
-      const float delta = red_a[0][row] + red_a[1][row];
-#pragma unroll
-      for (int j = 0; j < SC; ++j) pr[j] = pr[j] * (__uint_as_float(d[j]) - delta) * p.scale;
-#pragma unroll
-      for (int c0 = 0; c0 < SC; c0 += 8) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) split2_f16(pr[c0 + 2 * j], pr[c0 + 2 * j + 1], hi[j], lo[j]);
-        tmem_st4(tS + lane_off + (tap0 + c0) / 2, hi);
-        tmem_st4(tS + lane_off + TP / 2 + (tap0 + c0) / 2, lo);
-        *reinterpret_cast<uint4*>(tdst + (c0 >> 3) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(tdst + TIMG + (c0 >> 3) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      wait_st();
-    }
-    fence_proxy_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      fence_after_sync();
-      // dQ = dShi Khi + dSlo Khi + dShi Klo      (B = the K window seen MN-major: N = channels, K = taps)
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a0 = tS + (pass == 1 ? TP / 2 : 0);
-        const uint32_t b0 = smem_u32(pass == 2 ? sKlo : sKhi);
-#pragma unroll
-        for (int ks = 0; ks < TP / 16; ++ks)
-          mma_f16_ts(tdP, a0 + ks * 8, make_desc(b0 + ks * 2 * 128, 128, TP * 16), idesc_dq, (pass | ks) != 0);
-      }
-      // dKw (+)= dS^T_hi Qhi + dS^T_lo Qhi + dS^T_hi Qlo
-#pragma unroll
-      for (int pass = 0; pass < 3; ++pass) {
-        const uint32_t a0 = smem_u32(pass == 1 ? sTlo : sThi);
-        const uint32_t b0 = smem_u32(pass == 2 ? sQlo : sQhi);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          if (!(NAF_BWD_EXP & 2)) mma_f16_ss(tdK, make_desc(a0 + ks * 2 * 2048, 2048, 128), make_desc(b0 + ks * 2 * 128, 128, 128 * 16),
-                     idesc_dk, (tile | pass | ks) != 0);
-      }
-      commit(&mbar);
-    }
-    mbar_wait(&mbar, phase);
-    phase ^= 1;
-    fence_after_sync();
+      NAF_TR();   // E: all chunk MMAs complete
 
-    // ================= dQ -> global: this thread's 32 columns of its pixel row
-    {
-      uint32_t r[32];
-      tmem_ld32(tdP + lane_off + hf * 32, r);
-      wait_ld();
-      if (cur.valid) {
-        float* dst = p.dq + cur.pix * p.D + head * DQ + hf * 32;
+      // ================= dS = scale P (dP - delta): TMEM (A operand of dQ, hi | lo) and dS^T -> the T buffer
+      {
+        const uint32_t tS = tS0 + tb(tile) * Cfg::kTA;
+        uint32_t d[SC];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          stg_stream(dst + 4 * j, make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                              __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+        for (int c0 = 0; c0 < SC; c0 += 8) tmem_ld8(tdP + lane_off + hf * SC + c0, *reinterpret_cast<uint32_t(*)[8]>(&d[c0]));
+        wait_ld();
+        float dl = 0.f;
+#pragma unroll
+        for (int j = 0; j < SC; ++j) dl = fmaf(pr[j], __uint_as_float(d[j]), dl);
+        red_a[hf][row] = dl;
+        worker_sync();
+        const float delta = red_a[0][row] + red_a[1][row];
+#pragma unroll
+        for (int j = 0; j < SC; ++j) pr[j] = pr[j] * (__uint_as_float(d[j]) - delta) * p.scale;
+#pragma unroll
+        for (int c0 = 0; c0 < SC; c0 += 8) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split2_f16(pr[c0 + 2 * j], pr[c0 + 2 * j + 1], hi[j], lo[j]);
+          tmem_st4(tS + lane_off + (tap0 + c0) / 2, hi);
+          tmem_st4(tS + lane_off + TP / 2 + (tap0 + c0) / 2, lo);
+          *reinterpret_cast<uint4*>(tdst + (c0 >> 3) * 128) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(tdst + Cfg::kT + (c0 >> 3) * 128) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        wait_st();
       }
+      fence_proxy_async_smem();
+      fence_before_sync();   // dP was read and dS written: dQ may overwrite dP, and read dS, after this arrival
+      mbar_arrive(&bars.ds_ready);
+      NAF_TR();   // F: dS written
+
+      // the queries of the next tile go into the other Q buffer while the tensor core runs dQ / dKw
+      if (overlap && tile + 1 < ntiles) next_q(tile + 1);
+      mbar_wait(&bars.dq_done, tile & 1);
+      fence_after_sync();
+      NAF_TR();   // G: dQ / dKw complete
+
+      // ================= dQ -> global: this thread's 32 columns of its pixel row (a line of the output, four 32-byte
+      // stores; staging the tile in shared memory for whole-line warp stores was measured no faster)
+      {
+        uint32_t r[32];
+        tmem_ld32(tdP + lane_off + hf * 32, r);
+        wait_ld();
+        fence_before_sync();   // the next chunk step's arrival lets dP overwrite these columns
+        if (cur.valid) {
+          float* dst = p.dq + cur.pix * p.D + head * DQ + hf * 32;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * j + e]);
+            stg_stream8(dst + 8 * j, v);
+          }
+        }
+      }
+      if (!overlap && tile + 1 < ntiles) next_q(tile + 1);
+      cur = nxt;
+      NAF_TR();   // H: dQ stored
     }
-    fence_before_sync();   // ordered before the next tile's MMAs by its barriers
-    cur = nxt;
   }
+  // every MMA of the cell has completed (the workers waited for the last dq_done)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
 
   // ================= window gradients: TMEM lane = tap; one vector atomic per 4 elements
-  {
+  if (warp < NW / 32) {
     const bool live = row < K2 && !(NAF_BWD_EXP & 8);
     const int t = live ? row / K : 0, u = live ? row - (row / K) * K : 0;
     const int64_t cell = int64_t(b * p.h + wy0 + t) * p.w + wx0 + u;
@@ -474,8 +601,15 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   }
   fence_before_sync();
   __syncthreads();
+  NAF_TR();   // Z: window gradients sent
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
+
+#if NAF_BWD_EXP & 32
+extern "C" NAF_API int naf_debug_bwd_trace(long long* host) {
+  return int(cudaMemcpyFromSymbol(host, g_bwd_trace, sizeof(g_bwd_trace)));
+}
+#endif
 
 // ------------------------------------------------------------------------------------ host side
 namespace {
@@ -486,16 +620,32 @@ template <int TP>
 int launch_bwd_tc(const naf_xattn_bwd_params& p, cudaStream_t st) {
   auto kern = xattn_bwd_cell_tc_kernel<TP>;
   const int dv = p.C / p.heads;
-  // shared memory: K window + V region + Q, G chunk, T (hi / lo each).  The V region holds the whole value head
-  // when that fits beside the rest (K <= 7 always; K = 9 up to dv = 176), else one 64-channel chunk.
-  const int fixed = 2 * BwdCfg<TP>::kWin + 4 * PIXIMG + 2 * TIMG;
-  const int v_full = 2 * (dv / 8) * TP * 16;
-  const int v_resident = fixed + v_full <= 220 * 1024 ? 1 : 0;
-  const int smem = fixed + (v_resident ? v_full : 2 * BwdCfg<TP>::kWin);
+  // Shared memory: T, K window, V region, Q and G images (hi / lo each).  Preferences, as far as they fit:
+  // the whole value head resident (staged once per cell; else one 64-channel chunk restaged per tile and chunk),
+  // the upstream-gradient chunk double buffered (its MMAs run while the next chunk is staged), and a second Q
+  // image + S region ("overlap": the next tile's queries are staged and multiplied while dQ / dKw of this one run).
+  using Cfg = BwdCfg<TP>;
+  const int img = 2 * PIXIMG;
+  const int v_full = 2 * (dv / 8) * TP * 16, v_chunk = 2 * Cfg::kWin;
+  const int budget = 224 * 1024;
+  const bool tmem2 = 2 * Cfg::kTA + (Cfg::kTA > DQ ? Cfg::kTA : DQ) + DQ + dv <= 512;
+  auto need = [&](int vres, int gb, int ov) { return 2 * Cfg::kT + 2 * Cfg::kWin + (vres ? v_full : v_chunk) + (1 + ov) * img + gb * img; };
+  int v_resident = 0, gbufs = 1, overlap = 0;
+  const int prefs[4][3] = {{1, 2, 1}, {1, 2, 0}, {1, 1, 1}, {1, 1, 0}};
+  for (const auto& c : prefs) {
+    if ((c[2] && !tmem2) || need(c[0], c[1], c[2]) > budget) continue;
+    v_resident = c[0], gbufs = c[1], overlap = c[2];
+    break;
+  }
+#ifdef NAF_BWD_NO_OVERLAP
+  overlap = 0;
+#endif
+  const int smem = need(v_resident, gbufs, overlap);
   cudaError_t e = ensure_dyn_smem(kern, smem);
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn_bwd(cell-tc): smem opt-in failed: %s", cudaGetErrorString(e));
   const unsigned grid = unsigned(p.B) * p.h * p.w * p.heads;
-  kern<<<grid, NT, smem, st>>>(p, p.Ho / p.h, p.Wo / p.w, dv, v_resident);
+  kern<<<grid, NT, smem, st>>>(p, p.Ho / p.h, p.Wo / p.w, dv, v_resident, gbufs, overlap, magic_of(p.Wo / p.w), magic_of(p.rep_y),
+                               magic_of(p.rep_x));
   return check_launch("xattn_bwd_cell_tc");
 }
 
@@ -510,9 +660,9 @@ bool xattn_bwd_cell_tc_supported(const naf_xattn_bwd_params& p, const char** why
   const int tpa = (tp + 31) / 32 * 32;
   if (tpa + (tpa > DQ ? tpa : DQ) + DQ + dv > 512) { *why = "window and value head need more than 512 TMEM columns"; return false; }
   if ((p.Ho / p.h) * (p.Wo / p.w) < 64) { *why = "fewer than 64 pixels per cell"; return false; }
-  if (!aligned16(p.q) || !aligned16(p.k) || !aligned16(p.v) || !aligned16(p.dout) || !aligned16(p.dq) ||
-      !aligned16(p.dk) || !aligned16(p.dv) || (p.q_stride_b % 4) || (p.q_stride_y % 4) || (p.q_stride_x % 4)) {
-    *why = "pointers / strides not 16-byte aligned";
+  if (!aligned32(p.q) || !aligned16(p.k) || !aligned16(p.v) || !aligned32(p.dout) || !aligned32(p.dq) ||
+      !aligned16(p.dk) || !aligned16(p.dv) || (p.q_stride_b % 8) || (p.q_stride_y % 8) || (p.q_stride_x % 8)) {
+    *why = "pointers / strides not 32-byte (q, dout, dq) / 16-byte aligned";
     return false;
   }
   if (p.cos_y && !(aligned16(p.cos_y) && aligned16(p.sin_y) && aligned16(p.cos_x) && aligned16(p.sin_x))) {

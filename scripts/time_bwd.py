@@ -7,10 +7,11 @@ from naf_b200 import _lib, ops
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-for (B, C, Ho, h, K) in [(1, 128, 448, 28, 9), (1, 1024, 448, 28, 9), (1, 768, 896, 32, 7)]:
+for (B, C, Ho, h, K) in [(1, 128, 448, 28, 9), (1, 384, 448, 28, 9), (1, 1024, 448, 28, 9), (1, 768, 896, 32, 7)]:
     D, n = 256, 4
-    q = torch.randn(B, D, Ho, Ho, device=dev); k = torch.randn(B, D, h, h, device=dev)
-    v = torch.randn(B, C, h, h, device=dev); dout = torch.randn(B, C, Ho, Ho, device=dev)
+    # pixel-major storage (what the autograd functions hand over): no packing pass inside the timed call
+    q = torch.randn(B, Ho, Ho, D, device=dev).permute(0, 3, 1, 2); k = torch.randn(B, h, h, D, device=dev).permute(0, 3, 1, 2)
+    v = torch.randn(B, h, h, C, device=dev).permute(0, 3, 1, 2); dout = torch.randn(B, Ho, Ho, C, device=dev).permute(0, 3, 1, 2)
     tabs = naf_b200.RoPE(D, num_heads=n, base=100.0, rescale_coords=2.0).eval().to(dev).axis_tables(Ho, Ho)
     fn = lambda: ops.xattn_bwd(q, k, v, dout, n, K, rope_tables=tabs, algo=_lib.ALGO_CELL_TC)
     for _ in range(2): fn()
