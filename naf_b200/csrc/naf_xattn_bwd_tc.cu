@@ -106,7 +106,7 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" :
 template <int TP>
 __global__ void __launch_bounds__(NT, 1)
 xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_resident, int gbufs, int overlap,
-                         uint32_t m_rw, uint32_t m_ry, uint32_t m_rx) {
+                         uint32_t m_rw, uint32_t m_ry, uint32_t m_rx, int nsm) {
   using Cfg = BwdCfg<TP>;
   constexpr int SC = TP / 2;   // S / dP columns per thread
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -265,27 +265,6 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   };
 
   Px cur = px_of(0);
-  if (warp < NW / 32) {
-    load_q(0);
-    load_g(0, 0);
-    // K window: K-major [channel chunk c][tap n][16 B], zero rows for the padding taps
-    const float* kwin = p.k + (int64_t(b * p.h + wy0) * p.w + wx0) * p.D + head * DQ;
-    for (int i = tid; i < TP * KC; i += NW) {
-      const int n = i % TP, c = i / TP;
-      uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
-      if (n < K2) {
-        const int t = n / K, u = n - t * K;
-        float x[8];
-        const float4* src = reinterpret_cast<const float4*>(kwin + (int64_t(t) * p.w + u) * p.D + c * 8);
-        const float4 a = __ldg(src), bb = __ldg(src + 1);
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bb.x; x[5] = bb.y; x[6] = bb.z; x[7] = bb.w;
-        split8(x, hi, lo);
-      }
-      *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
-      *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
-    }
-    fence_proxy_async_smem();
-  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -305,10 +284,62 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   auto gpar = [&](int s) { return uint32_t(gbufs == 2 ? (s >> 1) & 1 : s & 1); };
 
   if (warp >= NW / 32) {
-    // ================================================================ MMA thread
+    // ================================================================ MMA warp group
     // 12 warps start with 168 registers each; this group hands its share to the workers
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    // The group's 128 threads stage the cell's windows while the workers load and stage the first queries and
+    // upstream gradients; only the issuing thread depends on them (the workers never read K or a resident V).
+    {
+      // K window: K-major [channel chunk c][tap n][16 B], zero rows for the padding taps
+      const float* kwin = p.k + (int64_t(b * p.h + wy0) * p.w + wx0) * p.D + head * DQ;
+      for (int i = tid - NW; i < TP * KC; i += NT - NW) {
+        const int n = i % TP, c = i / TP;
+        uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
+        if (n < K2) {
+          const int t = n / K, u = n - t * K;
+          float x[8];
+          const float4* src = reinterpret_cast<const float4*>(kwin + (int64_t(t) * p.w + u) * p.D + c * 8);
+          const float4 a = __ldg(src), bb = __ldg(src + 1);
+          x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = bb.x; x[5] = bb.y; x[6] = bb.z; x[7] = bb.w;
+          split8(x, hi, lo);
+        }
+        *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
+        *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
+      }
+      // resident value head: the whole V window [channel group][tap][16 B], loads batched four deep
+      if (v_resident) {
+        const int nv = TP * (dv >> 3);
+        for (int i0 = tid - NW; i0 < nv; i0 += 4 * (NT - NW)) {
+          float4 va[4], vb[4];
+  #pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * (NT - NW), n = i % TP, g8 = i / TP;
+            va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < nv && n < K2) {
+              const int t = n / K, u = n - t * K;
+              const float4* src = reinterpret_cast<const float4*>(vwin + (int64_t(t) * p.w + u) * p.C + g8 * 8);
+              va[k] = __ldg(src);
+              vb[k] = __ldg(src + 1);
+            }
+          }
+  #pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int i = i0 + k * (NT - NW);
+            if (i < nv) {
+              const float x[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
+              uint4 hi, lo;
+              split8(x, hi, lo);
+              *reinterpret_cast<uint4*>(sVhi + i * 16) = hi;
+              *reinterpret_cast<uint4*>(sVlo + i * 16) = lo;
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, %0;" ::"n"(NT - NW) : "memory");
+    }
     if (warp == NW / 32 && lane == 0) {
+      fence_after_sync();
       auto issue_s = [&](int t) {
         // S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T
         mbar_wait(&bars.q_ready[tb(t)], tpar(t));
@@ -390,6 +421,25 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   } else {
     // ================================================================ workers: two threads per pixel row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    load_q(0);
+    load_g(0, 0);
+    // The first loads of a cell pay a cold miss (measured: ~5 us before the first softmax can start, TLB included).
+    // CTAs are handed out in index order, so the cell this SM most likely runs next is nsm CTAs further: its first
+    // tile's query and upstream-gradient lines are pulled into L2 now, a whole cell's time ahead.  A wrong guess costs
+    // 128 KB of L2 traffic.
+    if (int(blockIdx.x) + nsm < int(gridDim.x) && cur.valid && !(NAF_BWD_EXP & 64)) {
+      int nb = blockIdx.x + nsm;
+      const int nhead = nb % p.heads;
+      nb /= p.heads;
+      const int ncj = nb % p.w;
+      nb /= p.w;
+      const int nci = nb % p.h, nbb = nb / p.h;
+      const int ny = nci * rh + (cur.y - y0), nx = ncj * rw + (cur.x - x0);
+      prefetch_l2(p.q + int64_t(nbb) * p.q_stride_b + int64_t(magic_div(ny, p.rep_y, m_ry)) * p.q_stride_y +
+                  int64_t(magic_div(nx, p.rep_x, m_rx)) * p.q_stride_x + nhead * DQ + hf * 32);
+      const char* gp = reinterpret_cast<const char*>(p.dout + ((int64_t(nbb) * p.Ho + ny) * p.Wo + nx) * p.C + nhead * dv);
+      for (int off = hf * 128; off < dv * 4; off += 256) prefetch_l2(gp + off);
+    }
     const int tap0 = hf * SC;
     uint8_t* const tdst = sThi + (row >> 3) * Cfg::kPG + (tap0 >> 3) * 128 + (row & 7) * 16;
     auto next_q = [&](int t) {      // stage the queries of tile t, start loading those of tile t + 1
@@ -424,10 +474,10 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
         }
         if (c + 1 < nchunks) load_g(tile, c + 1);
         else if (tile + 1 < ntiles) load_g(tile + 1, 0);
-        // V window chunk: K-major [channel group][tap][16 B] (once per cell when the value head is resident)
-        if (tile == 0 || !v_resident) {
-          uint8_t* const vhi = sVhi + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
-          uint8_t* const vlo = sVlo + (v_resident ? c * (DVC / 8) * TP * 16 : 0);
+        // V window chunk of a value head that is not resident: K-major [channel group][tap][16 B]
+        if (!v_resident) {
+          uint8_t* const vhi = sVhi;
+          uint8_t* const vlo = sVlo;
           constexpr int VIT = (TP * 8 + NW - 1) / NW;     // items per thread at the full chunk width
           float4 va[VIT], vb[VIT];
 #pragma unroll
@@ -645,7 +695,7 @@ int launch_bwd_tc(const naf_xattn_bwd_params& p, cudaStream_t st) {
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn_bwd(cell-tc): smem opt-in failed: %s", cudaGetErrorString(e));
   const unsigned grid = unsigned(p.B) * p.h * p.w * p.heads;
   kern<<<grid, NT, smem, st>>>(p, p.Ho / p.h, p.Wo / p.w, dv, v_resident, gbufs, overlap, magic_of(p.Wo / p.w), magic_of(p.rep_y),
-                               magic_of(p.rep_x));
+                               magic_of(p.rep_x), device_sm_count());
   return check_launch("xattn_bwd_cell_tc");
 }
 

@@ -7,5 +7,5 @@ tail -14 $out/check_bwd_tc.log
 timeout 400 python -m pytest tests/test_gpu_backward.py -x -q -m gpu > $out/pytest_bwd.log 2>&1
 tail -5 $out/pytest_bwd.log
 NAF_B200_LIB=scripts/exp/libnaf_bwdtrace.so timeout 100 python scripts/trace_bwd.py > $out/trace.log 2>&1
-{ timeout 100 python scripts/time_bwd.py; NAF_B200_LIB=scripts/exp/libnaf_bwdnoov.so timeout 100 python scripts/time_bwd.py; } > $out/time_bwd.log 2>&1
+{ timeout 100 python scripts/time_bwd.py; NAF_B200_LIB=scripts/exp/libnaf_bwdnopf.so timeout 100 python scripts/time_bwd.py; } > $out/time_bwd.log 2>&1
 cat $out/time_bwd.log
