@@ -72,6 +72,22 @@ __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, fl
 __host__ __device__ __forceinline__ uint32_t magic_of(int d) { return d > 1 ? uint32_t(((1ull << 32) + uint32_t(d) - 1) / uint32_t(d)) : 0u; }
 __device__ __forceinline__ int magic_div(int n, int d, uint32_t magic) { return d > 1 ? int(__umulhi(uint32_t(n), magic)) : n; }
 
+// One lane of a converged warp.  Under elect.sync the compiler knows that exactly one thread runs the guarded region and
+// keeps the MMA descriptors in uniform registers, where UTCHMMA reads them: back-to-back MMAs in the SASS.  Under
+// `lane == 0` every MMA is preceded by R2UR moves and an election loop on one thread's dependent chain (measured ~85
+// clocks per N = 64 MMA, more than the tensor core needs).  The 128-tap instantiation (heavy register spills in the
+// issuing thread) faulted with it on the GPU and keeps the plain form.
+template <bool kElect>
+__device__ __forceinline__ bool elect_one() {
+  if constexpr (kElect) {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+  } else {
+    return (threadIdx.x & 31) == 0;
+  }
+}
+
 // 32-byte global load that stays where it is written (register prefetch: the compiler must not sink it to its use)
 __device__ __forceinline__ void ldg8_keep(const float* p, float (&r)[8]) {
   asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -106,7 +122,7 @@ __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" :
 template <int TP>
 __global__ void __launch_bounds__(NT, 1)
 xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_resident, int gbufs, int overlap,
-                         uint32_t m_rw, uint32_t m_ry, uint32_t m_rx, int nsm) {
+                         uint32_t m_rw, uint32_t m_ry, uint32_t m_rx) {
   using Cfg = BwdCfg<TP>;
   constexpr int SC = TP / 2;   // S / dP columns per thread
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -127,7 +143,9 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
   uint8_t* sQ = sVlo + v_img;                              // (1 + overlap) x (hi, lo) images of the rotated queries
   uint8_t* sG = sQ + (1 + overlap) * (2 * PIXIMG);         // gbufs x (hi, lo) images of the upstream-gradient chunk
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the warp index through a shuffle: provably warp-uniform, so that the role branches below are uniform branches
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int rowgrp = warp & 3, hf = (warp >> 2) & 1;
   const int row = rowgrp * 32 + lane;
   const int K = p.K, K2 = K * K;
@@ -215,8 +233,11 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
       }
     }
   };
-  float g8r[4][8];           // block k * 8 + warp of the chunk: 8 pixels x one quad of channel groups
-  auto load_g = [&](int tile, int c) {
+  // Upstream-gradient chunks are loaded TWO chunk steps ahead when the registers allow (up to 64 taps): a step is
+  // ~1.5 us, about one HBM round trip under load, and with one step of lead every step waited for its loads.
+  constexpr bool kDeepG = TP <= 64;
+  float g8r[kDeepG ? 2 : 1][4][8];     // [set][block k * 8 + warp of the chunk: 8 pixels x one quad of channel groups]
+  auto load_g = [&](int tile, int c, float (&g8r)[4][8]) {
     const int ng = min(DVC, dv - c * DVC) >> 3;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -338,21 +359,38 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, %0;" ::"n"(NT - NW) : "memory");
     }
-    if (warp == NW / 32 && lane == 0) {
+#ifdef NAF_BWD_LANE0
+    constexpr bool kElect = false;
+#else
+    constexpr bool kElect = TP <= 96;
+#endif
+    __syncwarp();
+    if (warp == NW / 32 && elect_one<kElect>()) {
       fence_after_sync();
+      // Descriptors are built once and advanced by adding to their address field (bits 0..13, 16-byte units; no carry
+      // can leave it: shared memory ends below 2^18 bytes).
+      auto adv = [](uint64_t d, uint32_t bytes) { return d + (bytes >> 4); };
+      const uint64_t dKk = make_desc(smem_u32(sKhi), TP * 16, 128);        // K window, K-major (B of S)
+      const uint64_t dKm = make_desc(smem_u32(sKhi), 128, TP * 16);        // K window, MN-major (B of dQ)
+      const uint64_t dVk = make_desc(smem_u32(sVhi), TP * 16, 128);        // V window, K-major (B of dP)
+      const uint64_t dT = make_desc(smem_u32(sThi), Cfg::kPG, 128);        // P^T / dS^T, MN-major (A of dVw, dKw)
+      const uint64_t dQk0 = make_desc(smem_u32(sQ), 128 * 16, 128);        // Q image 0, K-major (A of S)
+      const uint64_t dQm0 = make_desc(smem_u32(sQ), 128, 128 * 16);        // Q image 0, MN-major (B of dKw)
+      const uint64_t dGk0 = make_desc(smem_u32(sG), 128 * 16, 128);        // G image 0, K-major (A of dP)
+      const uint64_t dGm0 = make_desc(smem_u32(sG), 128, 128 * 16);        // G image 0, MN-major (B of dVw)
+      const uint32_t v_lo = uint32_t(v_img);                               // hi -> lo image of the V window
       auto issue_s = [&](int t) {
         // S = Qhi Khi^T + Qlo Khi^T + Qhi Klo^T
         mbar_wait(&bars.q_ready[tb(t)], tpar(t));
         fence_after_sync();
-        const uint32_t qhi = smem_u32(sQ + tb(t) * (2 * PIXIMG)), qlo = qhi + PIXIMG;
+        const uint64_t qa = adv(dQk0, tb(t) * (2 * PIXIMG));
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = pass == 1 ? qlo : qhi;
-          const uint32_t b0 = smem_u32(pass == 2 ? sKlo : sKhi);
+          const uint64_t a0 = adv(qa, pass == 1 ? PIXIMG : 0);
+          const uint64_t b0 = adv(dKk, pass == 2 ? Cfg::kWin : 0);
 #pragma unroll
           for (int ks = 0; ks < DQ / 16; ++ks)
-            mma_f16_ss(tS0 + tb(t) * Cfg::kTA, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
-                       make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (pass | ks) != 0);
+            mma_f16_ss(tS0 + tb(t) * Cfg::kTA, adv(a0, ks * 2 * (128 * 16)), adv(b0, ks * 2 * (TP * 16)), idesc_s, (pass | ks) != 0);
         }
         commit(&bars.s_done[tb(t)]);
       };
@@ -361,18 +399,19 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
       for (int t = 0; t < ntiles; ++t) {
         for (int c = 0; c < nchunks; ++c, ++s) {
           const int wc = min(DVC, dv - c * DVC);
-          const uint32_t ghi = smem_u32(sG + gb(s) * (2 * PIXIMG)), glo = ghi + PIXIMG;
-          const uint32_t vhi = smem_u32(sVhi + (v_resident ? c * (DVC / 8) * TP * 16 : 0));
-          const uint32_t vlo = smem_u32(sVlo + (v_resident ? c * (DVC / 8) * TP * 16 : 0));
+          const uint64_t gk = adv(dGk0, gb(s) * (2 * PIXIMG)), gm = adv(dGm0, gb(s) * (2 * PIXIMG));
+          const uint64_t vk = adv(dVk, v_resident ? c * (DVC / 8) * TP * 16 : 0);
           mbar_wait(&bars.g_ready[gb(s)], gpar(s));
           fence_after_sync();
           // dP (+)= Ghi Vhi^T + Glo Vhi^T + Ghi Vlo^T
+#pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a0 = pass == 1 ? glo : ghi;
-            const uint32_t b0 = pass == 2 ? vlo : vhi;
-            for (int ks = 0; ks < (wc >> 4); ++ks)
-              if (!(NAF_BWD_EXP & 4)) mma_f16_ss(tdP, make_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128),
-                         make_desc(b0 + ks * 2 * (TP * 16), TP * 16, 128), idesc_s, (c | pass | ks) != 0);
+            const uint64_t a0 = adv(gk, pass == 1 ? PIXIMG : 0);
+            const uint64_t b0 = adv(vk, pass == 2 ? v_lo : 0);
+#pragma unroll
+            for (int ks = 0; ks < DVC / 16; ++ks)
+              if (ks < (wc >> 4) && !(NAF_BWD_EXP & 4))
+                mma_f16_ss(tdP, adv(a0, ks * 2 * (128 * 16)), adv(b0, ks * 2 * (TP * 16)), idesc_s, (c | pass | ks) != 0);
           }
           if (c == 0) {
             mbar_wait(&bars.pt_ready, t & 1);
@@ -380,38 +419,37 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
           }
           // dVw[:, chunk] (+)= P^T_hi Ghi + P^T_lo Ghi + P^T_hi Glo   (A = P^T MN-major, B = G seen MN-major: K = pixels)
           const uint32_t idesc_dv = make_idesc_f16(128, wc, true, true);
+#pragma unroll
           for (int pass = 0; pass < 3; ++pass) {
-            const uint32_t a0 = smem_u32(pass == 1 ? sTlo : sThi);
-            const uint32_t b0 = pass == 2 ? glo : ghi;
+            const uint64_t a0 = adv(dT, pass == 1 ? Cfg::kT : 0);
+            const uint64_t b0 = adv(gm, pass == 2 ? PIXIMG : 0);
 #pragma unroll
             for (int ks = 0; ks < 8; ++ks)
-              if (!(NAF_BWD_EXP & 1)) mma_f16_ss(tdV + c * DVC, make_desc(a0 + ks * 2 * Cfg::kPG, Cfg::kPG, 128),
-                         make_desc(b0 + ks * 2 * 128, 128, 128 * 16), idesc_dv, (t | pass | ks) != 0);
+              if (!(NAF_BWD_EXP & 1)) mma_f16_ss(tdV + c * DVC, adv(a0, ks * 2 * Cfg::kPG), adv(b0, ks * 2 * 128), idesc_dv, (t | pass | ks) != 0);
           }
           commit(&bars.g_done[gb(s)]);
         }
         mbar_wait(&bars.ds_ready, t & 1);
         fence_after_sync();
         const uint32_t tS = tS0 + tb(t) * Cfg::kTA;
-        const uint32_t qhi = smem_u32(sQ + tb(t) * (2 * PIXIMG)), qlo = qhi + PIXIMG;
         // dQ = dShi Khi + dSlo Khi + dShi Klo      (B = the K window seen MN-major: N = channels, K = taps)
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
           const uint32_t a0 = tS + (pass == 1 ? TP / 2 : 0);
-          const uint32_t b0 = smem_u32(pass == 2 ? sKlo : sKhi);
+          const uint64_t b0 = adv(dKm, pass == 2 ? Cfg::kWin : 0);
 #pragma unroll
           for (int ks = 0; ks < TP / 16; ++ks)
-            mma_f16_ts(tdP, a0 + ks * 8, make_desc(b0 + ks * 2 * 128, 128, TP * 16), idesc_dq, (pass | ks) != 0);
+            mma_f16_ts(tdP, a0 + ks * 8, adv(b0, ks * 2 * 128), idesc_dq, (pass | ks) != 0);
         }
         // dKw (+)= dS^T_hi Qhi + dS^T_lo Qhi + dS^T_hi Qlo
+        const uint64_t qm = adv(dQm0, tb(t) * (2 * PIXIMG));
 #pragma unroll
         for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = smem_u32(pass == 1 ? sTlo : sThi);
-          const uint32_t b0 = pass == 2 ? qlo : qhi;
+          const uint64_t a0 = adv(dT, pass == 1 ? Cfg::kT : 0);
+          const uint64_t b0 = adv(qm, pass == 2 ? PIXIMG : 0);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            if (!(NAF_BWD_EXP & 2)) mma_f16_ss(tdK, make_desc(a0 + ks * 2 * Cfg::kPG, Cfg::kPG, 128), make_desc(b0 + ks * 2 * 128, 128, 128 * 16),
-                       idesc_dk, (t | pass | ks) != 0);
+            if (!(NAF_BWD_EXP & 2)) mma_f16_ss(tdK, adv(a0, ks * 2 * Cfg::kPG), adv(b0, ks * 2 * 128), idesc_dk, (t | pass | ks) != 0);
         }
         commit(&bars.dq_done);
         if (t + 1 < ntiles) issue_s(t + 1);
@@ -422,23 +460,10 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
     // ================================================================ workers: two threads per pixel row
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     load_q(0);
-    load_g(0, 0);
-    // The first loads of a cell pay a cold miss (measured: ~5 us before the first softmax can start, TLB included).
-    // CTAs are handed out in index order, so the cell this SM most likely runs next is nsm CTAs further: its first
-    // tile's query and upstream-gradient lines are pulled into L2 now, a whole cell's time ahead.  A wrong guess costs
-    // 128 KB of L2 traffic.
-    if (int(blockIdx.x) + nsm < int(gridDim.x) && cur.valid && !(NAF_BWD_EXP & 64)) {
-      int nb = blockIdx.x + nsm;
-      const int nhead = nb % p.heads;
-      nb /= p.heads;
-      const int ncj = nb % p.w;
-      nb /= p.w;
-      const int nci = nb % p.h, nbb = nb / p.h;
-      const int ny = nci * rh + (cur.y - y0), nx = ncj * rw + (cur.x - x0);
-      prefetch_l2(p.q + int64_t(nbb) * p.q_stride_b + int64_t(magic_div(ny, p.rep_y, m_ry)) * p.q_stride_y +
-                  int64_t(magic_div(nx, p.rep_x, m_rx)) * p.q_stride_x + nhead * DQ + hf * 32);
-      const char* gp = reinterpret_cast<const char*>(p.dout + ((int64_t(nbb) * p.Ho + ny) * p.Wo + nx) * p.C + nhead * dv);
-      for (int off = hf * 128; off < dv * 4; off += 256) prefetch_l2(gp + off);
+    load_g(0, 0, g8r[0]);
+    if constexpr (kDeepG) {
+      if (nchunks > 1) load_g(0, 1, g8r[1]);
+      else load_g(1, 0, g8r[1]);
     }
     const int tap0 = hf * SC;
     uint8_t* const tdst = sThi + (row >> 3) * Cfg::kPG + (tap0 >> 3) * 128 + (row & 7) * 16;
@@ -461,19 +486,24 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
         // the MMAs that read this G buffer (step gstep - gbufs) must have completed; with one buffer this also frees
         // the V chunk buffer of a value head that is not resident
         if (gstep >= gbufs) mbar_wait(&bars.g_done[gb(gstep - gbufs)], gpar(gstep - gbufs));
-        // G chunk (prefetched): K-major [channel group][row][16 B]
+        // G chunk (prefetched): K-major [channel group][row][16 B]; then the loads of the chunk 1 or 2 steps ahead
+        auto stage_g = [&](float (&set)[4][8]) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int bi = k * 8 + warp, g8 = (bi >> 4) * 4 + lg;
-          if (g8 < (wc >> 3)) {
-            uint4 hi, lo;
-            split8(g8r[k], hi, lo);
-            *reinterpret_cast<uint4*>(sGhi + (g8 * 128 + (bi & 15) * 8 + lp) * 16) = hi;
-            *reinterpret_cast<uint4*>(sGlo + (g8 * 128 + (bi & 15) * 8 + lp) * 16) = lo;
+          for (int k = 0; k < 4; ++k) {
+            const int bi = k * 8 + warp, g8 = (bi >> 4) * 4 + lg;
+            if (g8 < (wc >> 3)) {
+              uint4 hi, lo;
+              split8(set[k], hi, lo);
+              *reinterpret_cast<uint4*>(sGhi + (g8 * 128 + (bi & 15) * 8 + lp) * 16) = hi;
+              *reinterpret_cast<uint4*>(sGlo + (g8 * 128 + (bi & 15) * 8 + lp) * 16) = lo;
+            }
           }
-        }
-        if (c + 1 < nchunks) load_g(tile, c + 1);
-        else if (tile + 1 < ntiles) load_g(tile + 1, 0);
+          int t2 = tile, c2 = c + (kDeepG ? 2 : 1);
+          while (c2 >= nchunks) c2 -= nchunks, ++t2;
+          load_g(t2, c2, set);     // (tiles past the last one load zeros)
+        };
+        if (kDeepG && (gstep & 1)) stage_g(g8r[kDeepG ? 1 : 0]);
+        else stage_g(g8r[0]);
         // V window chunk of a value head that is not resident: K-major [channel group][tap][16 B]
         if (!v_resident) {
           uint8_t* const vhi = sVhi;
@@ -695,7 +725,7 @@ int launch_bwd_tc(const naf_xattn_bwd_params& p, cudaStream_t st) {
   if (e != cudaSuccess) return fail(NAF_ERR_CUDA, "xattn_bwd(cell-tc): smem opt-in failed: %s", cudaGetErrorString(e));
   const unsigned grid = unsigned(p.B) * p.h * p.w * p.heads;
   kern<<<grid, NT, smem, st>>>(p, p.Ho / p.h, p.Wo / p.w, dv, v_resident, gbufs, overlap, magic_of(p.Wo / p.w), magic_of(p.rep_y),
-                               magic_of(p.rep_x), device_sm_count());
+                               magic_of(p.rep_x));
   return check_launch("xattn_bwd_cell_tc");
 }
 
