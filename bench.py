@@ -342,10 +342,11 @@ def other_paths(dev, peak):
     # ---- backward at the reference's own backward benchmark (test/backward_speed.py: B=1, 448 <- 28, K=9) and on
     # one C2 image (896 <- 32, K=7, C=768)
     for name, (B, C, to, lo, K) in {"bwd_ref_protocol_c384": (1, 384, 448, 28, 9), "bwd_c2_image": (1, 768, 896, 32, 7)}.items():
-        q = torch.randn(B, D, to, to, generator=g).to(dev)
-        k = torch.randn(B, D, lo, lo, generator=g).to(dev)
-        v = torch.randn(B, C, lo, lo, generator=g).to(dev)
-        dout = torch.randn(B, C, to, to, generator=g).to(dev)
+        # NCHW-shaped views over pixel-major storage, what the autograd functions hand over: no packing pass in the timed call
+        q = torch.randn(B, to, to, D, generator=g).to(dev).permute(0, 3, 1, 2)
+        k = torch.randn(B, lo, lo, D, generator=g).to(dev).permute(0, 3, 1, 2)
+        v = torch.randn(B, lo, lo, C, generator=g).to(dev).permute(0, 3, 1, 2)
+        dout = torch.randn(B, to, to, C, generator=g).to(dev).permute(0, 3, 1, 2)
         tabs = naf_b200.RoPE(D, num_heads=4, base=100.0, rescale_coords=2.0).eval().to(dev).axis_tables(to, to)
         n0 = ops.launch_count("xattn_bwd_cell_tc")
         ms_b = time_op(lambda: ops.xattn_bwd(q, k, v, dout, 4, K, rope_tables=tabs))

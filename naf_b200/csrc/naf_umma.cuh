@@ -76,42 +76,13 @@ __device__ __forceinline__ void commit(uint64_t* mbar) {
                : "memory");
 }
 
-// The same, predicated: EVERY lane of the issuing warp runs the surrounding (converged) code, so that descriptors and
-// addresses are warp-uniform values the compiler keeps in uniform registers -- which is where UTCHMMA reads them.
-// Under a divergent `if (lane == 0)` they live in vector registers and each MMA pays several R2UR moves on one
-// thread's dependent chain (measured: ~85 clocks per N = 64 MMA, above the tensor core's own time).
-__device__ __forceinline__ void mma_f16_ss_p(uint32_t lead, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(lead)
-      : "memory");
-}
-__device__ __forceinline__ void mma_f16_ts_p(uint32_t lead, uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
-                                             uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p, q;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(lead)
-      : "memory");
-}
-__device__ __forceinline__ void commit_p(uint32_t lead, uint64_t* mbar) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
-      "}\n" ::"r"(smem_u32(mbar)), "r"(lead)
-      : "memory");
+// One lane of a converged warp.  Under elect.sync the compiler knows that exactly one thread runs the guarded region and
+// keeps the MMA descriptors in uniform registers, where UTCHMMA reads them (back-to-back MMAs in the SASS); under
+// `lane == 0` every MMA is preceded by R2UR moves and an election loop on one thread's dependent chain.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- TMEM --------------------------------------------------------------------------------------

@@ -237,7 +237,8 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
   float* const lsum = mx + 2 * 2 * 128;                             // [tile & 3][half][row]
   const float* const sTab = reinterpret_cast<const float*>(smem + Cfg::kSmemBytes);   // [K buffer][tab_bytes]
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches are uniform branches
   const int rh = gm.rh, rw = gm.rw;
   const int npix = rh * rw;
   const int ntiles = gm.ntiles;
@@ -743,7 +744,14 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
     }
   } else {
     // ======================================================================== MMA ISSUER
-    if (lane == 0) {
+#ifndef NAF_TMA_ELECT
+// 1: issue under elect.sync (descriptors in uniform registers: back-to-back UTCHMMA, what the backward kernel uses).
+// Measured here (session 4, same box): C2 unchanged (4.29 / 4.34 vs 4.29 / 4.31 ms), C3 SLOWER (5.99 / 6.06 vs 5.59 /
+// 5.63 ms: the faster issuer runs the next tile's Q K^T ahead of the P V the drain is waiting for).  Off.
+#define NAF_TMA_ELECT 0
+#endif
+    __syncwarp();
+    if (NAF_TMA_ELECT ? elect_one_sync() : lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc_f16(128, TP, false, false);
       constexpr uint32_t idesc_pv = make_idesc_f16(128, DVH, false, true);
       constexpr int QS = Cfg::kQStages;
