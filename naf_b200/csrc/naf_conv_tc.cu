@@ -565,7 +565,12 @@ conv128_ws_kernel(ConvParams p) {
 
   uint8_t* sW = smem + Ws::W_OFF;
   uint8_t* sStage = smem + Ws::STAGE_OFF;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+#if NAF_CONV_ELECT_DISABLE_SHFL
+  const int warp = tid >> 5;
+#else
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: the role branches are uniform branches
+#endif
   const int tiles_per_img = p.tiles_y * p.tiles_x;
   const int total = p.B * tiles_per_img;
 
@@ -784,7 +789,11 @@ conv128_ws_kernel(ConvParams p) {
     }
   } else if (warp == WC_MMA_WARP) {
     // ============================================================================= MMA ISSUER
-    if (lane == 0) {
+#ifndef NAF_CONV_ELECT
+#define NAF_CONV_ELECT 1   // 1: issue under elect.sync (descriptors in uniform registers), 0: under lane == 0
+#endif
+    __syncwarp();
+    if (NAF_CONV_ELECT ? elect_one_sync() : lane == 0) {
       constexpr uint32_t idesc = make_idesc_f16(128, CC, false, false);
       const uint32_t w_base = smem_u32(sW);
       constexpr int NS = Ws::NSLOT;
