@@ -787,7 +787,10 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
         commit(&bar_s_full[s]);
         if (last_of_item) commit(&bar_k_free[kb]);   // every MMA reading this K window has been issued
       };
-      auto issue_pv = [&](int g) {
+#ifndef NAF_TMA_QK_MID
+#define NAF_TMA_QK_MID 0   // 1: value heads in several accumulator halves issue the next tile's Q K^T after the FIRST half
+#endif                     //    (it then runs while that half drains) instead of before the whole P V
+      auto issue_pv = [&](int g, bool qk_mid) {
         const int s = g & 1;
         mbar_wait(&bar_p_full[s], (g >> 1) & 1);
         const int vb = Cfg::NVB == 2 ? (pv_seq & 1) : 0;
@@ -817,13 +820,15 @@ xattn_cell_tma_kernel(naf_xattn_params p, TmGeom gm, TmDivs dv, const __grid_con
             }
           }
           commit(&bar_o_full[ob]);
+          if (qk_mid && hh == 0) issue_qk(g + 1);
         }
         if (last_of_item) commit(&bar_v_free[vb]);
       };
       if (total_tiles > 0) issue_qk(0);
+      constexpr bool kMid = NAF_TMA_QK_MID && NH >= 2;
       for (int g = 0; g < total_tiles; ++g) {
-        if (g + 1 < total_tiles) issue_qk(g + 1);
-        issue_pv(g);
+        if (!kMid && g + 1 < total_tiles) issue_qk(g + 1);
+        issue_pv(g, kMid && g + 1 < total_tiles);
       }
     }
     __syncwarp();
