@@ -75,8 +75,7 @@ __device__ __forceinline__ int magic_div(int n, int d, uint32_t magic) { return 
 // One lane of a converged warp.  Under elect.sync the compiler knows that exactly one thread runs the guarded region and
 // keeps the MMA descriptors in uniform registers, where UTCHMMA reads them: back-to-back MMAs in the SASS.  Under
 // `lane == 0` every MMA is preceded by R2UR moves and an election loop on one thread's dependent chain (measured ~85
-// clocks per N = 64 MMA, more than the tensor core needs).  The 128-tap instantiation (heavy register spills in the
-// issuing thread) faulted with it on the GPU and keeps the plain form.
+// clocks per N = 64 MMA, more than the tensor core needs).
 template <bool kElect>
 __device__ __forceinline__ bool elect_one() {
   if constexpr (kElect) {
@@ -359,10 +358,10 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
       fence_proxy_async_smem();
       asm volatile("bar.sync 2, %0;" ::"n"(NT - NW) : "memory");
     }
-#ifdef NAF_BWD_LANE0
-    constexpr bool kElect = false;
+#if defined(NAF_BWD_LANE0)
+    constexpr bool kElect = false;   // profiling: the plain form
 #else
-    constexpr bool kElect = TP <= 96;
+    constexpr bool kElect = true;
 #endif
     __syncwarp();
     if (warp == NW / 32 && elect_one<kElect>()) {

@@ -118,6 +118,7 @@ GRAD_CASES = [
     (1, 256, 4, 4, 768, 98, 98, (1, 1), 7, 7, 7),      # C2-like cells (r=14, dv=192): tensor-core kernel, 3 value chunks
     (1, 256, 4, 4, 768, 88, 88, (1, 1), 11, 11, 11),   # K=11, dv=192: tensor-core kernel with all 512 TMEM columns
     (2, 256, 4, 4, 384, 72, 90, (1, 1), 9, 9, 9),      # the backward benchmark's K=9, dv=96 (chunks of 64 + 32), r=8x10
+    (1, 256, 4, 4, 768, 56, 56, (2, 2), 4, 4, 3),      # 7-tile cells (r=28) behind replicated guidance: second Q image / S region, 3 chunks
 ]
 
 
