@@ -21,6 +21,12 @@
 // of the summed pixels do not average out relative to the sum.)  P^T and dS^T share one buffer (P^T is dead
 // once the last dVw chunk has been issued and completed).
 // The value head is walked in chunks of 64 channels (G and Vw chunks are staged together: one pass over G).
+//
+// Roles (384 threads): 8 worker warps, two threads per pixel row (global loads, RoPE, split-fp16 staging of Q / G, the
+// two softmax phases, dS, the dQ store, the window-gradient atomics); one MMA warp group whose 128 threads stage the
+// K / V windows and whose ONE elected thread issues every MMA.  Eleven mbarriers carry the hand-offs (BwdBars); the
+// upstream-gradient chunk is double buffered and, where shared memory and TMEM allow, a second Q image / S region lets
+// the next tile's S run under dQ / dKw of the current one.  setmaxnreg moves registers from the MMA group to the workers.
 #include "naf_common.cuh"
 #include "naf_umma.cuh"
 
