@@ -24,7 +24,7 @@
 //
 // Roles (384 threads): 8 worker warps, two threads per pixel row (global loads, RoPE, split-fp16 staging of Q / G, the
 // two softmax phases, dS, the dQ store, the window-gradient atomics); one MMA warp group whose 128 threads stage the
-// K / V windows and whose ONE elected thread issues every MMA.  Eleven mbarriers carry the hand-offs (BwdBars); the
+// K / V windows and whose ONE elected thread issues every MMA.  Twelve mbarriers carry the hand-offs (BwdBars); the
 // upstream-gradient chunk is double buffered and, where shared memory and TMEM allow, a second Q image / S region lets
 // the next tile's S run under dQ / dKw of the current one.  setmaxnreg moves registers from the MMA group to the workers.
 #include "naf_common.cuh"
@@ -120,6 +120,7 @@ struct BwdBars {
   uint64_t g_done[2];     // dP / dVw MMAs of a chunk step complete      (tensor core -> workers)
   uint64_t ds_ready;      // dS in TMEM, dS^T in shared memory           (workers -> MMA thread)
   uint64_t dq_done;       // dQ / dKw of the tile complete               (tensor core -> workers)
+  uint64_t v_ready;       // resident V window staged                    (warps 9-11 -> MMA thread)
 };
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NW) : "memory"); }
@@ -182,6 +183,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
     mbar_init(&bars.g_done[1], 1);
     mbar_init(&bars.ds_ready, NW);
     mbar_init(&bars.dq_done, 1);
+    mbar_init(&bars.v_ready, NT - NW - 32);
     fence_mbar_init();
   }
   const bool rope = p.cos_y != nullptr;
@@ -313,8 +315,10 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
     // ================================================================ MMA warp group
     // 12 warps start with 168 registers each; this group hands its share to the workers
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-    // The group's 128 threads stage the cell's windows while the workers load and stage the first queries and
-    // upstream gradients; only the issuing thread depends on them (the workers never read K or a resident V).
+    // The group stages the cell's windows while the workers load and stage the first queries and upstream gradients;
+    // only the issuing thread depends on them (the workers never read K or a resident V).  All 128 threads stage K;
+    // then the issuing warp starts S of the first tile while the other three warps stage the (larger) V window, which
+    // the first dP needs a whole softmax later.
     {
       // K window: K-major [channel chunk c][tap n][16 B], zero rows for the padding taps
       const float* kwin = p.k + (int64_t(b * p.h + wy0) * p.w + wx0) * p.D + head * DQ;
@@ -332,14 +336,17 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
         *reinterpret_cast<uint4*>(sKhi + (c * TP + n) * 16) = hi;
         *reinterpret_cast<uint4*>(sKlo + (c * TP + n) * 16) = lo;
       }
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 2, %0;" ::"n"(NT - NW) : "memory");
       // resident value head: the whole V window [channel group][tap][16 B], loads batched four deep
-      if (v_resident) {
+      constexpr int NV = NT - NW - 32;     // threads of warps 9 .. 11
+      if (v_resident && warp > NW / 32) {
         const int nv = TP * (dv >> 3);
-        for (int i0 = tid - NW; i0 < nv; i0 += 4 * (NT - NW)) {
+        for (int i0 = tid - NW - 32; i0 < nv; i0 += 4 * NV) {
           float4 va[4], vb[4];
   #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int i = i0 + k * (NT - NW), n = i % TP, g8 = i / TP;
+            const int i = i0 + k * NV, n = i % TP, g8 = i / TP;
             va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < nv && n < K2) {
               const int t = n / K, u = n - t * K;
@@ -350,7 +357,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
           }
   #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int i = i0 + k * (NT - NW);
+            const int i = i0 + k * NV;
             if (i < nv) {
               const float x[8] = {va[k].x, va[k].y, va[k].z, va[k].w, vb[k].x, vb[k].y, vb[k].z, vb[k].w};
               uint4 hi, lo;
@@ -360,9 +367,9 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
             }
           }
         }
+        fence_proxy_async_smem();
+        mbar_arrive(&bars.v_ready);
       }
-      fence_proxy_async_smem();
-      asm volatile("bar.sync 2, %0;" ::"n"(NT - NW) : "memory");
     }
 #if defined(NAF_BWD_LANE0)
     constexpr bool kElect = false;   // profiling: the plain form
@@ -407,6 +414,7 @@ xattn_bwd_cell_tc_kernel(naf_xattn_bwd_params p, int rh, int rw, int dv, int v_r
           const uint64_t gk = adv(dGk0, gb(s) * (2 * PIXIMG)), gm = adv(dGm0, gb(s) * (2 * PIXIMG));
           const uint64_t vk = adv(dVk, v_resident ? c * (DVC / 8) * TP * 16 : 0);
           mbar_wait(&bars.g_ready[gb(s)], gpar(s));
+          if (s == 0 && v_resident) mbar_wait(&bars.v_ready, 0);
           fence_after_sync();
           // dP (+)= Ghi Vhi^T + Glo Vhi^T + Ghi Vlo^T
 #pragma unroll
