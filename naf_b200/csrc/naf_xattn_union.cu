@@ -147,6 +147,10 @@ xattn_union_tc_kernel(naf_xattn_params p, UnionGeom g) {
   uint8_t* sVlo = sVhi + NC * dvp * 2;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifndef NAF_UNION_ELECT
+#define NAF_UNION_ELECT 1   // 1: the MMAs are issued under elect.sync (descriptors in uniform registers), 0: by lane 0
+#endif
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (see naf_umma.cuh:elect_one_sync)
   const int rowgrp = warp & 3;      // TMEM lane quarter this warp may touch
   const int hf = warp >> 2;         // which half of the columns this thread owns
   const int row = rowgrp * 32 + lane;
@@ -326,7 +330,7 @@ xattn_union_tc_kernel(naf_xattn_params p, UnionGeom g) {
     fence_proxy_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0 && (NAF_UNION_ELECT ? elect_one_sync() : lane == 0)) {
       fence_after_sync();
       // S = Qhi*Khi^T + Qlo*Khi^T + Qhi*Klo^T
       for (int pass = 0; pass < 3; ++pass) {
@@ -360,7 +364,7 @@ xattn_union_tc_kernel(naf_xattn_params p, UnionGeom g) {
     fence_before_sync();
     __syncthreads();
     l_run = l_run * alpha + red_l[0][row] + red_l[1][row];
-    if (tid == 0) {
+    if (warp_u == 0 && (NAF_UNION_ELECT ? elect_one_sync() : lane == 0)) {
       fence_after_sync();
       // O (+)= Phi*Vhi + Plo*Vhi + Phi*Vlo
       for (int pass = 0; pass < 3; ++pass) {
